@@ -1,0 +1,324 @@
+"""B200-native PairHMM forward engine -- Python face of libphmm_b200.so (ctypes over include/phmm.h).
+
+Only the read x haplotype likelihood path of avis9ditiu/gatk-haplotypecaller-cpp17 lives here
+(reference: src/haplotypecaller/pairhmm/intel_pairhmm.hpp).  `PairHMMEngine.compute_likelihoods`
+mirrors `hc::IntelPairHMM::compute_likelihoods` (:48-56): log10 likelihood matrix [reads][haps],
+capped at best-4.5 per read, poorly modelled reads erased (:24-46).
+
+There is NO CPU fallback: importing works without a GPU (so the library's symbols can be checked),
+but every compute call raises PhmmError unless an sm_100 device and the compiled extension are
+present.  The directory name is not a valid module name; load it with `__graft_entry__.load_package()`.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libphmm_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+PHMM_OK = 0
+ERR_NAMES = {1: "INVALID_ARG", 2: "NO_DEVICE", 3: "CUDA", 4: "OOM", 5: "UNSUPPORTED", 6: "BAD_TICKET"}
+
+
+class PhmmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"phmm error {code} ({ERR_NAMES.get(code, '?')}): {msg}")
+        self.code = code
+
+
+def build(verbose=False):
+    """Compile libphmm_b200.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    res = subprocess.run(["make", "-j8", "-C", CSRC], capture_output=True, text=True)
+    if verbose or res.returncode:
+        print(res.stdout[-4000:], res.stderr[-4000:])
+    if res.returncode:
+        raise RuntimeError("building libphmm_b200.so failed")
+    return LIB_PATH
+
+
+class _Options(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("n_devices", C.c_int32), ("devices", C.POINTER(C.c_int32)),
+                ("pipeline_depth", C.c_int32), ("exact_fp32", C.c_int32), ("host_threads", C.c_int32),
+                ("reserved", C.c_int32 * 3)]
+
+
+class _Batch(C.Structure):
+    _fields_ = [("n_regions", C.c_int32), ("n_reads", C.c_int32), ("n_haps", C.c_int32),
+                ("region_read_beg", C.c_void_p), ("region_hap_beg", C.c_void_p), ("read_off", C.c_void_p),
+                ("read_bases", C.c_void_p), ("read_q", C.c_void_p), ("read_i", C.c_void_p),
+                ("read_d", C.c_void_p), ("read_c", C.c_void_p), ("hap_off", C.c_void_p),
+                ("hap_bases", C.c_void_p),
+                ("gap_open_i", C.c_uint8), ("gap_open_d", C.c_uint8), ("gap_cont_c", C.c_uint8),
+                ("reserved0", C.c_uint8)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_pairs", C.c_int64), ("n_cells", C.c_int64), ("n_rescued", C.c_int64),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("kernel_launches", C.c_int32),
+                ("n_devices_used", C.c_int32), ("kernel_ms", C.c_float), ("total_ms", C.c_float)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class _Result(C.Structure):
+    _fields_ = [("log10_lik", C.c_void_p), ("raw32", C.c_void_p), ("raw64", C.c_void_p),
+                ("rescued", C.c_void_p), ("stats", Stats)]
+
+
+EXPORTS = ["phmm_create", "phmm_destroy", "phmm_compute", "phmm_submit", "phmm_wait", "phmm_strerror",
+           "phmm_last_error", "phmm_abi_version", "phmm_normalize_filter", "phmm_tables",
+           "phmm_stage", "phmm_run_staged", "phmm_fetch_staged", "phmm_free_staged"]
+
+_lib = None
+
+
+def lib():
+    """Load libphmm_b200.so; fails loudly if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PhmmError(-1, f"{LIB_PATH} is missing: run __graft_entry__.build() (there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.phmm_create.argtypes = [C.POINTER(_Options), C.POINTER(C.c_void_p)]
+        L.phmm_destroy.argtypes = [C.c_void_p]; L.phmm_destroy.restype = None
+        L.phmm_compute.argtypes = [C.c_void_p, C.POINTER(_Batch), C.POINTER(_Result)]
+        L.phmm_submit.argtypes = [C.c_void_p, C.POINTER(_Batch), C.POINTER(C.c_int64)]
+        L.phmm_wait.argtypes = [C.c_void_p, C.c_int64, C.POINTER(_Result)]
+        L.phmm_strerror.argtypes = [C.c_int]; L.phmm_strerror.restype = C.c_char_p
+        L.phmm_last_error.argtypes = [C.c_void_p]; L.phmm_last_error.restype = C.c_char_p
+        L.phmm_normalize_filter.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+        L.phmm_tables.argtypes = [C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.POINTER(C.c_float)),
+                                  C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.POINTER(C.c_double)),
+                                  C.POINTER(C.c_int32)]
+        L.phmm_stage.argtypes = [C.c_void_p, C.POINTER(_Batch), C.POINTER(C.c_void_p)]
+        L.phmm_run_staged.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
+        L.phmm_fetch_staged.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_Result)]
+        L.phmm_free_staged.argtypes = [C.c_void_p, C.c_void_p]; L.phmm_free_staged.restype = None
+        _lib = L
+    return _lib
+
+
+def host_tables():
+    """The host-built probability tables the kernels use (native/Context.h semantics)."""
+    L = lib()
+    pf, mf = C.POINTER(C.c_float)(), C.POINTER(C.c_float)()
+    pd, md = C.POINTER(C.c_double)(), C.POINTER(C.c_double)()
+    n = C.c_int32()
+    L.phmm_tables(C.byref(pf), C.byref(mf), C.byref(pd), C.byref(md), C.byref(n))
+    return {"ph2pr_f32": np.ctypeslib.as_array(pf, (128,)).copy(), "mm_f32": np.ctypeslib.as_array(mf, (n.value,)).copy(),
+            "ph2pr_f64": np.ctypeslib.as_array(pd, (128,)).copy(), "mm_f64": np.ctypeslib.as_array(md, (n.value,)).copy()}
+
+
+class Batch:
+    """SoA batch of active regions (the phmm_batch layout of include/phmm.h) held in numpy arrays."""
+
+    def __init__(self, region_read_beg, region_hap_beg, read_off, read_bases, read_q, hap_off, hap_bases,
+                 read_i=None, read_d=None, read_c=None, gap_open_i=ord("I"), gap_open_d=ord("I"), gap_cont_c=ord("+")):
+        a32 = lambda x: np.ascontiguousarray(x, dtype=np.int32)
+        a8 = lambda x: np.ascontiguousarray(x, dtype=np.uint8)
+        self.region_read_beg, self.region_hap_beg = a32(region_read_beg), a32(region_hap_beg)
+        self.read_off, self.hap_off = a32(read_off), a32(hap_off)
+        self.read_bases, self.read_q, self.hap_bases = a8(read_bases), a8(read_q), a8(hap_bases)
+        self.explicit_gaps = read_i is not None
+        n = len(self.read_bases)
+        # the checkers always want per-base arrays; the engine gets NULL + constants when uniform
+        self.read_i = a8(read_i) if read_i is not None else np.full(n, gap_open_i, np.uint8)
+        self.read_d = a8(read_d) if read_d is not None else np.full(n, gap_open_d, np.uint8)
+        self.read_c = a8(read_c) if read_c is not None else np.full(n, gap_cont_c, np.uint8)
+        self.gap_open_i, self.gap_open_d, self.gap_cont_c = gap_open_i, gap_open_d, gap_cont_c
+        self.n_regions = len(self.region_read_beg) - 1
+        self.n_reads = len(self.read_off) - 1
+        self.n_haps = len(self.hap_off) - 1
+
+    @property
+    def reads_per_region(self):
+        return np.diff(self.region_read_beg)
+
+    @property
+    def haps_per_region(self):
+        return np.diff(self.region_hap_beg)
+
+    @property
+    def region_out_beg(self):
+        return np.concatenate([[0], np.cumsum(self.reads_per_region.astype(np.int64) * self.haps_per_region)])
+
+    @property
+    def n_pairs(self):
+        return int(self.region_out_beg[-1])
+
+    @property
+    def n_cells(self):
+        rl = np.diff(self.read_off).astype(np.int64)
+        hl = np.diff(self.hap_off).astype(np.int64)
+        rsum = np.add.reduceat(rl, self.region_read_beg[:-1]) if self.n_reads else np.zeros(self.n_regions, np.int64)
+        hsum = np.add.reduceat(hl, self.region_hap_beg[:-1]) if self.n_haps else np.zeros(self.n_regions, np.int64)
+        rsum = np.where(self.reads_per_region > 0, rsum, 0)
+        hsum = np.where(self.haps_per_region > 0, hsum, 0)
+        return int((rsum * hsum).sum())
+
+    @property
+    def input_bytes(self):
+        per_base = 5 if self.explicit_gaps else 2
+        return int(per_base * len(self.read_bases) + len(self.hap_bases))
+
+    def c_struct(self):
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        b = _Batch()
+        b.n_regions, b.n_reads, b.n_haps = self.n_regions, self.n_reads, self.n_haps
+        b.region_read_beg, b.region_hap_beg = p(self.region_read_beg), p(self.region_hap_beg)
+        b.read_off, b.hap_off = p(self.read_off), p(self.hap_off)
+        b.read_bases, b.read_q, b.hap_bases = p(self.read_bases), p(self.read_q), p(self.hap_bases)
+        if self.explicit_gaps:
+            b.read_i, b.read_d, b.read_c = p(self.read_i), p(self.read_d), p(self.read_c)
+        else:
+            b.read_i = b.read_d = b.read_c = None
+        b.gap_open_i, b.gap_open_d, b.gap_cont_c = self.gap_open_i, self.gap_open_d, self.gap_cont_c
+        return b
+
+    @staticmethod
+    def from_regions(regions, **kw):
+        """regions: list of (reads, quals, haps[, ins, del, gcp]) with bytes / uint8 arrays."""
+        rrb, rhb, roff, hoff = [0], [0], [0], [0]
+        rb, rq, hb, ri, rd_, rc = [], [], [], [], [], []
+        explicit = any(len(reg) > 3 for reg in regions)
+        u8 = lambda x: np.frombuffer(x, np.uint8) if isinstance(x, (bytes, bytearray)) else np.asarray(x, np.uint8)
+        for reg in regions:
+            reads, quals, haps = reg[0], reg[1], reg[2]
+            for k, (s, q) in enumerate(zip(reads, quals)):
+                s, q = u8(s), u8(q)
+                assert len(s) == len(q)
+                rb.append(s); rq.append(q); roff.append(roff[-1] + len(s))
+                if explicit:
+                    ri.append(u8(reg[3][k])); rd_.append(u8(reg[4][k])); rc.append(u8(reg[5][k]))
+            for h in haps:
+                h = u8(h); hb.append(h); hoff.append(hoff[-1] + len(h))
+            rrb.append(len(roff) - 1); rhb.append(len(hoff) - 1)
+        cat = lambda xs: np.concatenate(xs) if xs else np.zeros(0, np.uint8)
+        if explicit:
+            kw.update(read_i=cat(ri), read_d=cat(rd_), read_c=cat(rc))
+        return Batch(rrb, rhb, roff, cat(rb), cat(rq), hoff, cat(hb), **kw)
+
+
+class Result:
+    def __init__(self, n_pairs, want_raw=True):
+        self.log10 = np.empty(n_pairs, np.float64)
+        self.raw32 = np.empty(n_pairs, np.float32) if want_raw else None
+        self.raw64 = np.empty(n_pairs, np.float64) if want_raw else None
+        self.rescued = np.empty(n_pairs, np.uint8) if want_raw else None
+        self._c = _Result()
+        p = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+        self._c.log10_lik, self._c.raw32, self._c.raw64, self._c.rescued = p(self.log10), p(self.raw32), p(self.raw64), p(self.rescued)
+
+    @property
+    def stats(self):
+        return self._c.stats.as_dict()
+
+
+class PairHMMEngine:
+    """Owns one phmm_engine (streams, memory pool, worker per device)."""
+
+    def __init__(self, devices=None, pipeline_depth=2, exact_fp32=False, host_threads=1):
+        self._L = lib()
+        opt = _Options()
+        opt.struct_size = C.sizeof(_Options)
+        devices = [0] if devices is None else list(devices)
+        self._dev_arr = (C.c_int32 * len(devices))(*devices)
+        opt.n_devices = len(devices)
+        opt.devices = C.cast(self._dev_arr, C.POINTER(C.c_int32))
+        opt.pipeline_depth, opt.exact_fp32, opt.host_threads = pipeline_depth, int(exact_fp32), host_threads
+        self._h = C.c_void_p()
+        rc = self._L.phmm_create(C.byref(opt), C.byref(self._h))
+        if rc != PHMM_OK:
+            raise PhmmError(rc, self._L.phmm_strerror(rc).decode())
+        self._inflight = {}
+
+    def _check(self, rc):
+        if rc != PHMM_OK:
+            raise PhmmError(rc, self._L.phmm_strerror(rc).decode() + ": " + self._L.phmm_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.phmm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- phmm_compute / phmm_submit / phmm_wait
+    def compute(self, batch, want_raw=True):
+        res = Result(batch.n_pairs, want_raw)
+        cb = batch.c_struct()
+        self._check(self._L.phmm_compute(self._h, C.byref(cb), C.byref(res._c)))
+        return res
+
+    def submit(self, batch):
+        t = C.c_int64()
+        cb = batch.c_struct()
+        self._check(self._L.phmm_submit(self._h, C.byref(cb), C.byref(t)))
+        self._inflight[t.value] = batch.n_pairs
+        return t.value
+
+    def wait(self, ticket, want_raw=False, result=None):
+        n = self._inflight.pop(ticket, 0)
+        res = result if result is not None else Result(n, want_raw)
+        self._check(self._L.phmm_wait(self._h, ticket, C.byref(res._c)))
+        return res
+
+    # -- device-resident form
+    def stage(self, batch):
+        st = C.c_void_p()
+        cb = batch.c_struct()
+        self._check(self._L.phmm_stage(self._h, C.byref(cb), C.byref(st)))
+        return st
+
+    def run_staged(self, st, iters=1):
+        ms, n = C.c_float(), C.c_int32()
+        self._check(self._L.phmm_run_staged(self._h, st, iters, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def fetch_staged(self, st, n_pairs, want_raw=True):
+        res = Result(n_pairs, want_raw)
+        self._check(self._L.phmm_fetch_staged(self._h, st, C.byref(res._c)))
+        return res
+
+    def free_staged(self, st):
+        self._L.phmm_free_staged(self._h, st)
+
+    # -- the reference's call surface: hc::IntelPairHMM::compute_likelihoods (intel_pairhmm.hpp:48-56)
+    def compute_likelihoods(self, haplotypes, reads, quals):
+        """haplotypes: list of bytes; reads/quals: lists of bytes (SEQ / QUAL, raw Phred+33).
+        Returns (matrix [kept][haps] float64, kept_indices).  Reads failing the poorly-modelled
+        filter are dropped, as the reference erases them from its `reads` vector (:40-45)."""
+        batch = Batch.from_regions([(reads, quals, haplotypes)])
+        res = self.compute(batch, want_raw=False)
+        lik = res.log10.reshape(len(reads), len(haplotypes)).copy()
+        keep = normalize_filter(lik, np.array([len(r) for r in reads], np.int32))
+        idx = np.nonzero(keep)[0]
+        return lik[idx], idx
+
+
+def normalize_filter(lik, read_len):
+    """In-place cap at best-4.5 and poorly-modelled-read flags (intel_pairhmm.hpp:24-46), host side."""
+    lik = np.ascontiguousarray(lik, np.float64)
+    n_reads, n_haps = lik.shape
+    keep = np.zeros(n_reads, np.uint8)
+    rl = np.ascontiguousarray(read_len, np.int32)
+    lib().phmm_normalize_filter(lik.ctypes.data_as(C.c_void_p), n_reads, n_haps,
+                                rl.ctypes.data_as(C.c_void_p), keep.ctypes.data_as(C.c_void_p))
+    return keep
+
+
+from . import synth  # noqa: E402,F401

@@ -1,0 +1,874 @@
+// phmm_engine.cu -- host side of libphmm_b200.so: the C ABI of include/phmm.h.
+//
+// Replaces, for the PairHMM path only, what hc::IntelPairHMM does around its AVX kernels
+// (pairhmm/intel_pairhmm.hpp): initNative (:77-113), getData (:154-203), the FP32 -> FP64
+// dispatch loop (:115-152) and the log10 conversion (:139,:142).  Differences by design:
+//   * many regions per batch, all pairs of a batch in flight at once (the reference walks
+//     reads x haplotypes serially, one region at a time, haplotypecaller.hpp:138-152);
+//   * per-device memory pool (grow-only pinned + device arenas per pipeline slot) and one stream
+//     per slot, so batch N+1 packs/uploads while batch N computes and batch N-1 downloads;
+//   * regions are sharded over devices by cell count with no exchange between devices (every
+//     pair is independent, intel_pairhmm.hpp:131-147); results are gathered on the host;
+//   * raw forward sums come back from the device and log10f/log10 run on the HOST with glibc,
+//     because the reference's final value is (double)(log10f(f) - log10f(2^120)) evaluated in
+//     float (:142) and device log10f differs from glibc in the last ulp.
+// No CPU fallback: every entry point fails with a CUDA error when no device is usable.
+#include "../../include/phmm.h"
+#include "phmm_launch.h"
+#include "phmm_tables.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cfloat>
+#include <chrono>
+#include <cmath>
+#include <condition_variable>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace phmm;
+
+namespace {
+
+constexpr size_t kAlign = 256;
+inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
+
+struct KernelTable {
+    // [f64][exact][uniform][K-1]
+    KernelFn fn[2][2][2][kMaxRowsPerLane];
+    KernelTable() {
+        register_f32_fast(fn[0][0]);
+        register_f32_exact(fn[0][1]);
+        register_f64_fast(fn[1][0]);
+        register_f64_exact(fn[1][1]);
+    }
+};
+const KernelTable& kernel_table() { static KernelTable t; return t; }
+
+// rows per lane for a read of R bases: K*G >= R + 1 (at least one dummy row on top)
+inline int rows_per_lane(int R) { return (R + 1 + kGroupWidth - 1) / kGroupWidth; }
+constexpr int kMaxReadLenCompiled = kMaxRowsPerLane * kGroupWidth - 1;   // 255
+
+// ---- grow-only buffers (the memory pool) ----------------------------------------------------
+struct PinnedBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = std::max(n, (size_t)1 << 20);
+        want = want + want / 4;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+struct DeviceBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = std::max(n, (size_t)1 << 20);
+        want = want + want / 4;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// ---- one device's share of a batch: a contiguous range of regions -----------------------------
+struct Part {
+    int g0 = 0, g1 = 0;                       // region range in the caller's batch
+    int n_regions = 0, n_reads = 0, n_haps = 0;
+    int64_t n_pairs = 0, n_cells = 0, out0 = 0;   // out0: offset of this part in the batch output
+    bool uniform = true;
+    int max_H = 0, max_nh = 0;
+    int n_jobs = 0;
+    int job_beg[kMaxRowsPerLane + 1] = {0};
+    int haps_per_job = 1, hap_chunks = 1;
+    size_t h2d_bytes = 0, d2h_bytes = 0;
+    int launches = 0;
+    float kernel_ms = 0.f;
+    unsigned rescue_count = 0;
+};
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
+    PinnedBuf h_in, h_out, h_rescue;
+    DeviceBuf d_in, d_out, d_rescue;
+    bool busy = false;
+    Part part;
+    KernelArgs args{};
+};
+
+struct phmm_engine_impl;
+
+struct DeviceCtx {
+    int ordinal = 0;
+    int sm_count = 148;
+    std::vector<Slot> slots;
+    int next_slot = 0;
+    float* d_ph2pr_f = nullptr; float* d_mm_f = nullptr;
+    double* d_ph2pr_d = nullptr; double* d_mm_d = nullptr;
+    // worker
+    std::thread worker;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<std::function<void()>> queue;
+    bool stop = false;
+
+    void run() {
+        cudaSetDevice(ordinal);
+        for (;;) {
+            std::function<void()> fn;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stop || !queue.empty(); });
+                if (queue.empty()) return;
+                fn = std::move(queue.front());
+                queue.pop_front();
+            }
+            fn();
+        }
+    }
+    void post(std::function<void()> fn) {
+        { std::lock_guard<std::mutex> lk(mu); queue.push_back(std::move(fn)); }
+        cv.notify_one();
+    }
+};
+
+struct Latch {
+    std::mutex mu; std::condition_variable cv; int remaining;
+    explicit Latch(int n) : remaining(n) {}
+    void done() { std::lock_guard<std::mutex> lk(mu); if (--remaining == 0) cv.notify_all(); }
+    void wait() { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return remaining == 0; }); }
+};
+
+struct TicketRec {
+    std::vector<std::pair<int, int>> parts;   // (device index, slot index)
+    int64_t n_pairs = 0;
+    std::chrono::steady_clock::time_point t0;
+};
+
+}  // namespace
+
+struct phmm_engine {
+    phmm_options opt{};
+    std::vector<std::unique_ptr<DeviceCtx>> devs;
+    std::mutex mu;
+    std::string last_error;
+    std::map<phmm_ticket, TicketRec> tickets;
+    phmm_ticket next_ticket = 1;
+    int host_threads = 1;
+
+    void set_error(const std::string& s) { std::lock_guard<std::mutex> lk(mu); last_error = s; }
+};
+
+struct phmm_staged {
+    int dev_index = 0;
+    Slot slot;           // private buffers, not part of the pipeline ring
+    bool ran = false;
+};
+
+namespace {
+
+#define CUDA_TRY(expr)                                                                            \
+    do {                                                                                          \
+        cudaError_t e__ = (expr);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            err = std::string(#expr) + ": " + cudaGetErrorString(e__);                            \
+            return PHMM_ERR_CUDA;                                                                 \
+        }                                                                                         \
+    } while (0)
+
+int validate_batch(const phmm_batch* b, std::string& err)
+{
+    if (!b) { err = "batch is NULL"; return PHMM_ERR_INVALID_ARG; }
+    if (b->n_regions < 0 || b->n_reads < 0 || b->n_haps < 0) { err = "negative count"; return PHMM_ERR_INVALID_ARG; }
+    if (b->n_regions == 0) return PHMM_OK;
+    if (!b->region_read_beg || !b->region_hap_beg || !b->read_off || !b->hap_off) {
+        err = "NULL offset array"; return PHMM_ERR_INVALID_ARG;
+    }
+    if ((b->n_reads && (!b->read_bases || !b->read_q)) || (b->n_haps && !b->hap_bases)) {
+        err = "NULL base/quality array"; return PHMM_ERR_INVALID_ARG;
+    }
+    const bool any_gap = b->read_i || b->read_d || b->read_c;
+    if (any_gap && !(b->read_i && b->read_d && b->read_c)) {
+        err = "read_i/read_d/read_c must be all set or all NULL"; return PHMM_ERR_INVALID_ARG;
+    }
+    if (b->region_read_beg[0] != 0 || b->region_hap_beg[0] != 0 ||
+        b->region_read_beg[b->n_regions] != b->n_reads || b->region_hap_beg[b->n_regions] != b->n_haps) {
+        err = "region ranges must cover [0,n_reads) and [0,n_haps)"; return PHMM_ERR_INVALID_ARG;
+    }
+    for (int g = 0; g < b->n_regions; g++)
+        if (b->region_read_beg[g + 1] < b->region_read_beg[g] || b->region_hap_beg[g + 1] < b->region_hap_beg[g]) {
+            err = "region ranges not monotone"; return PHMM_ERR_INVALID_ARG;
+        }
+    for (int r = 0; r < b->n_reads; r++) {
+        int R = b->read_off[r + 1] - b->read_off[r];
+        if (R < 1) { err = "empty read"; return PHMM_ERR_INVALID_ARG; }
+        if (R > kMaxReadLenCompiled) { err = "read longer than " + std::to_string(kMaxReadLenCompiled); return PHMM_ERR_UNSUPPORTED; }
+    }
+    for (int h = 0; h < b->n_haps; h++) {
+        int H = b->hap_off[h + 1] - b->hap_off[h];
+        if (H < 1) { err = "empty haplotype"; return PHMM_ERR_INVALID_ARG; }
+        if (H > PHMM_MAX_HAP_LEN) { err = "haplotype longer than PHMM_MAX_HAP_LEN"; return PHMM_ERR_UNSUPPORTED; }
+    }
+    return PHMM_OK;
+}
+
+int64_t batch_pairs(const phmm_batch* b, int g0, int g1)
+{
+    int64_t n = 0;
+    for (int g = g0; g < g1; g++)
+        n += (int64_t)(b->region_read_beg[g + 1] - b->region_read_beg[g]) * (b->region_hap_beg[g + 1] - b->region_hap_beg[g]);
+    return n;
+}
+
+int64_t region_cells(const phmm_batch* b, int g)
+{
+    int r0 = b->region_read_beg[g], r1 = b->region_read_beg[g + 1];
+    int h0 = b->region_hap_beg[g], h1 = b->region_hap_beg[g + 1];
+    return (int64_t)(b->read_off[r1] - b->read_off[r0]) * (b->hap_off[h1] - b->hap_off[h0]);
+}
+
+// Pack regions [g0,g1) of the batch into the slot's pinned block, upload, launch, start D2H.
+int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1, int64_t out0,
+                     bool exact, bool do_launch, std::string& err)
+{
+    Part& p = s.part;
+    p = Part();
+    p.g0 = g0; p.g1 = g1; p.out0 = out0;
+    p.n_regions = g1 - g0;
+    const int r0 = b->region_read_beg[g0], r1 = b->region_read_beg[g1];
+    const int h0 = b->region_hap_beg[g0], h1 = b->region_hap_beg[g1];
+    p.n_reads = r1 - r0; p.n_haps = h1 - h0;
+    p.n_pairs = batch_pairs(b, g0, g1);
+    if (p.n_pairs == 0) return PHMM_OK;
+    const int rb0 = b->read_off[r0], rb1 = b->read_off[r1];
+    const int hb0 = b->hap_off[h0], hb1 = b->hap_off[h1];
+    const size_t read_bytes = (size_t)(rb1 - rb0), hap_bytes = (size_t)(hb1 - hb0);
+
+    // uniform gap penalties? (always, for the reference's own callers: sam/sam.hpp:30-32)
+    std::vector<uchar4> gap(p.n_reads);
+    p.uniform = true;
+    if (!b->read_i) {
+        for (auto& gq : gap) gq = make_uchar4(b->gap_open_i, b->gap_open_d, b->gap_cont_c, 0);
+    } else {
+        for (int r = r0; r < r1 && p.uniform; r++) {
+            const int o = b->read_off[r], R = b->read_off[r + 1] - o;
+            const uint8_t i0 = b->read_i[o], d0 = b->read_d[o], c0 = b->read_c[o];
+            for (int k = 1; k < R; k++)
+                if (b->read_i[o + k] != i0 || b->read_d[o + k] != d0 || b->read_c[o + k] != c0) { p.uniform = false; break; }
+            gap[r - r0] = make_uchar4(i0, d0, c0, 0);
+        }
+    }
+
+    // ---- plan: per region, reads of equal K are scored two at a time ----
+    std::vector<WarpJob> jobs_k[kMaxRowsPerLane];
+    for (int g = g0; g < g1; g++) {
+        int pending[kMaxRowsPerLane];
+        for (int k = 0; k < kMaxRowsPerLane; k++) pending[k] = -1;
+        const int nh = b->region_hap_beg[g + 1] - b->region_hap_beg[g];
+        p.max_nh = std::max(p.max_nh, nh);
+        if (nh == 0) continue;
+        int64_t hap_sum = b->hap_off[b->region_hap_beg[g + 1]] - b->hap_off[b->region_hap_beg[g]];
+        for (int r = b->region_read_beg[g]; r < b->region_read_beg[g + 1]; r++) {
+            const int R = b->read_off[r + 1] - b->read_off[r];
+            p.n_cells += (int64_t)R * hap_sum;
+            const int k = rows_per_lane(R) - 1;
+            if (pending[k] < 0) { pending[k] = r - r0; continue; }
+            WarpJob j; j.region = g - g0; j.read[0] = pending[k]; j.read[1] = r - r0; j.read[2] = j.read[3] = -1;
+            jobs_k[k].push_back(j);
+            pending[k] = -1;
+        }
+        for (int k = 0; k < kMaxRowsPerLane; k++)
+            if (pending[k] >= 0) {
+                WarpJob j; j.region = g - g0; j.read[0] = pending[k]; j.read[1] = j.read[2] = j.read[3] = -1;
+                jobs_k[k].push_back(j);
+            }
+    }
+    for (int h = h0; h < h1; h++) p.max_H = std::max(p.max_H, b->hap_off[h + 1] - b->hap_off[h]);
+    p.n_jobs = 0;
+    for (int k = 0; k < kMaxRowsPerLane; k++) { p.job_beg[k] = p.n_jobs; p.n_jobs += (int)jobs_k[k].size(); }
+    p.job_beg[kMaxRowsPerLane] = p.n_jobs;
+    {   // enough (job, hap-chunk) units to fill the chip several times over
+        const int64_t target = (int64_t)dc.sm_count * 16 * 6;
+        int chunks = (int)std::min<int64_t>(std::max<int64_t>(1, (target + p.n_jobs - 1) / std::max(1, p.n_jobs)), std::max(1, p.max_nh));
+        p.haps_per_job = (std::max(1, p.max_nh) + chunks - 1) / chunks;
+        p.hap_chunks = (std::max(1, p.max_nh) + p.haps_per_job - 1) / p.haps_per_job;
+    }
+
+    // ---- layout of the upload block ----
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
+    const size_t o_read_off = take(sizeof(int32_t) * (p.n_reads + 1));
+    const size_t o_hap_off  = take(sizeof(int32_t) * (p.n_haps + 1));
+    const size_t o_reg_read = take(sizeof(int32_t) * (p.n_regions + 1));
+    const size_t o_reg_hap  = take(sizeof(int32_t) * (p.n_regions + 1));
+    const size_t o_reg_out  = take(sizeof(int64_t) * (p.n_regions + 1));
+    const size_t o_bases    = take(read_bytes);
+    const size_t o_q        = take(read_bytes);
+    const size_t o_gi       = p.uniform ? 0 : take(read_bytes);
+    const size_t o_gd       = p.uniform ? 0 : take(read_bytes);
+    const size_t o_gc       = p.uniform ? 0 : take(read_bytes);
+    const size_t o_gap      = p.uniform ? take(sizeof(uchar4) * p.n_reads) : 0;
+    const size_t o_haps     = take(hap_bytes);
+    const size_t o_jobs     = take(sizeof(WarpJob) * p.n_jobs);
+    const size_t in_bytes   = off;
+
+    CUDA_TRY(s.h_in.reserve(in_bytes));
+    CUDA_TRY(s.d_in.reserve(in_bytes));
+    const size_t out_bytes = 16 + sizeof(float) * (size_t)p.n_pairs;
+    CUDA_TRY(s.h_out.reserve(out_bytes));
+    CUDA_TRY(s.d_out.reserve(out_bytes));
+    CUDA_TRY(s.d_rescue.reserve(sizeof(RescueOut) * (size_t)p.n_pairs));
+
+    uint8_t* hp = (uint8_t*)s.h_in.p;
+    {
+        int32_t* ro = (int32_t*)(hp + o_read_off);
+        for (int r = 0; r <= p.n_reads; r++) ro[r] = b->read_off[r0 + r] - rb0;
+        int32_t* ho = (int32_t*)(hp + o_hap_off);
+        for (int h = 0; h <= p.n_haps; h++) ho[h] = b->hap_off[h0 + h] - hb0;
+        int32_t* rr = (int32_t*)(hp + o_reg_read);
+        int32_t* rh = (int32_t*)(hp + o_reg_hap);
+        int64_t* rout = (int64_t*)(hp + o_reg_out);
+        int64_t acc = 0;
+        for (int g = 0; g <= p.n_regions; g++) {
+            rr[g] = b->region_read_beg[g0 + g] - r0;
+            rh[g] = b->region_hap_beg[g0 + g] - h0;
+            rout[g] = acc;
+            if (g < p.n_regions)
+                acc += (int64_t)(b->region_read_beg[g0 + g + 1] - b->region_read_beg[g0 + g]) *
+                       (b->region_hap_beg[g0 + g + 1] - b->region_hap_beg[g0 + g]);
+        }
+        std::memcpy(hp + o_bases, b->read_bases + rb0, read_bytes);
+        std::memcpy(hp + o_q, b->read_q + rb0, read_bytes);
+        if (!p.uniform) {
+            std::memcpy(hp + o_gi, b->read_i + rb0, read_bytes);
+            std::memcpy(hp + o_gd, b->read_d + rb0, read_bytes);
+            std::memcpy(hp + o_gc, b->read_c + rb0, read_bytes);
+        } else {
+            std::memcpy(hp + o_gap, gap.data(), sizeof(uchar4) * p.n_reads);
+        }
+        std::memcpy(hp + o_haps, b->hap_bases + hb0, hap_bytes);
+        WarpJob* jd = (WarpJob*)(hp + o_jobs);
+        for (int k = 0; k < kMaxRowsPerLane; k++)
+            if (!jobs_k[k].empty()) std::memcpy(jd + p.job_beg[k], jobs_k[k].data(), sizeof(WarpJob) * jobs_k[k].size());
+    }
+
+    uint8_t* dp = (uint8_t*)s.d_in.p;
+    KernelArgs& a = s.args;
+    a.read_off = (const int32_t*)(dp + o_read_off);
+    a.hap_off = (const int32_t*)(dp + o_hap_off);
+    a.region_read_beg = (const int32_t*)(dp + o_reg_read);
+    a.region_hap_beg = (const int32_t*)(dp + o_reg_hap);
+    a.region_out_beg = (const int64_t*)(dp + o_reg_out);
+    a.read_bases = dp + o_bases;
+    a.read_q = dp + o_q;
+    a.read_i = p.uniform ? nullptr : dp + o_gi;
+    a.read_d = p.uniform ? nullptr : dp + o_gd;
+    a.read_c = p.uniform ? nullptr : dp + o_gc;
+    a.read_gap = p.uniform ? (const uchar4*)(dp + o_gap) : nullptr;
+    a.hap_bases = dp + o_haps;
+    a.ph2pr_f = dc.d_ph2pr_f; a.mm_f = dc.d_mm_f; a.ph2pr_d = dc.d_ph2pr_d; a.mm_d = dc.d_mm_d;
+    a.jobs = (const WarpJob*)(dp + o_jobs);
+    a.n_jobs = 0;
+    a.haps_per_job = p.haps_per_job;
+    a.smem_words_per_warp = (p.max_H + 31) / 32 * 32 + 32;
+    a.rescue_count = (unsigned*)s.d_out.p;
+    a.raw32 = (float*)((uint8_t*)s.d_out.p + 16);
+    a.rescue_out = (RescueOut*)s.d_rescue.p;
+
+    CUDA_TRY(cudaMemcpyAsync(s.d_in.p, s.h_in.p, in_bytes, cudaMemcpyHostToDevice, s.stream));
+    p.h2d_bytes = in_bytes;
+    if (!do_launch) return PHMM_OK;
+
+    auto launch_all = [&](bool f64) -> int {
+        const size_t smem = sizeof(uint32_t) * (size_t)a.smem_words_per_warp * kWarpsPerCta;
+        for (int k = 0; k < kMaxRowsPerLane; k++) {
+            const int n = p.job_beg[k + 1] - p.job_beg[k];
+            if (n == 0) continue;
+            KernelFn fn = kernel_table().fn[f64 ? 1 : 0][exact ? 1 : 0][p.uniform ? 1 : 0][k];
+            KernelArgs ak = a;
+            ak.jobs = a.jobs + p.job_beg[k];
+            ak.n_jobs = n;
+            if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            dim3 grid((n + kWarpsPerCta - 1) / kWarpsPerCta, p.hap_chunks);
+            fn<<<grid, kWarpsPerCta * 32, smem, s.stream>>>(ak);
+            CUDA_TRY(cudaGetLastError());
+            p.launches++;
+        }
+        return PHMM_OK;
+    };
+    CUDA_TRY(cudaMemsetAsync(s.d_out.p, 0, 16, s.stream));
+    CUDA_TRY(cudaEventRecord(s.ev_k0, s.stream));
+    int rc = launch_all(false); if (rc) return rc;
+    rc = launch_all(true); if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(s.ev_k1, s.stream));
+    CUDA_TRY(cudaMemcpyAsync(s.h_out.p, s.d_out.p, out_bytes, cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(cudaEventRecord(s.ev_done, s.stream));
+    p.d2h_bytes = out_bytes;
+    return PHMM_OK;
+}
+
+// Wait for the slot, fetch the rescue list if any, convert raw sums to log10 (intel_pairhmm.hpp:137-143).
+int finalize_part(phmm_engine* e, DeviceCtx& dc, Slot& s, phmm_result* r, std::string& err)
+{
+    (void)dc;
+    Part& p = s.part;
+    if (p.n_pairs == 0) return PHMM_OK;
+    CUDA_TRY(cudaEventSynchronize(s.ev_done));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1));
+    p.kernel_ms = ms;
+    const unsigned count = *(const unsigned*)s.h_out.p;
+    p.rescue_count = count;
+    const float* raw32 = (const float*)((const uint8_t*)s.h_out.p + 16);
+    if (count > (uint64_t)p.n_pairs) { err = "rescue counter overflow"; return PHMM_ERR_CUDA; }
+    if (count) {
+        CUDA_TRY(s.h_rescue.reserve(sizeof(RescueOut) * (size_t)count));
+        CUDA_TRY(cudaMemcpyAsync(s.h_rescue.p, s.d_rescue.p, sizeof(RescueOut) * (size_t)count, cudaMemcpyDeviceToHost, s.stream));
+        CUDA_TRY(cudaStreamSynchronize(s.stream));
+        p.d2h_bytes += sizeof(RescueOut) * (size_t)count;
+    }
+    const Tables& T = host_tables();
+    double* out = r->log10_lik + p.out0;
+    float* o32 = r->raw32 ? r->raw32 + p.out0 : nullptr;
+    double* o64 = r->raw64 ? r->raw64 + p.out0 : nullptr;
+    uint8_t* ores = r->rescued ? r->rescued + p.out0 : nullptr;
+    const float log10_init_f = T.log10_init_f;
+    std::atomic<int64_t> need_rescue{0};
+    auto body = [&](int64_t i0, int64_t i1) {
+        int64_t nr = 0;
+        for (int64_t i = i0; i < i1; i++) {
+            const float f = raw32[i];
+            if (f < kMinAccepted) { nr++; out[i] = std::nan(""); }
+            else out[i] = (double)(log10f(f) - log10_init_f);       // float subtraction, :142
+            if (o32) o32[i] = f;
+            if (o64) o64[i] = 0.0;
+            if (ores) ores[i] = 0;
+        }
+        need_rescue += nr;
+    };
+    const int nt = (int)std::min<int64_t>(e->host_threads, std::max<int64_t>(1, p.n_pairs / 65536));
+    if (nt <= 1) body(0, p.n_pairs);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++)
+            th.emplace_back(body, p.n_pairs * t / nt, p.n_pairs * (t + 1) / nt);
+        for (auto& x : th) x.join();
+    }
+    if ((uint64_t)need_rescue.load() != count) {
+        err = "rescue list size " + std::to_string(count) + " != FP32 underflows " + std::to_string(need_rescue.load());
+        return PHMM_ERR_CUDA;
+    }
+    const RescueOut* rl = (const RescueOut*)s.h_rescue.p;
+    for (unsigned k = 0; k < count; k++) {
+        const int64_t i = rl[k].out_idx;
+        double d = rl[k].raw64;
+        // x86 FTZ also flushes double denormals (MXCSR, intel_pairhmm.hpp:102-105); the device
+        // keeps them, so flush the final sum here.
+        if (d < DBL_MIN) d = 0.0;
+        out[i] = std::log10(d) - T.log10_init_d;                     // :139
+        if (o64) o64[i] = d;
+        if (ores) ores[i] = 1;
+    }
+    return PHMM_OK;
+}
+
+int init_device(DeviceCtx& dc, int depth, std::string& err)
+{
+    CUDA_TRY(cudaSetDevice(dc.ordinal));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dc.ordinal));
+    if (prop.major < 10) { err = "device is not sm_100 or newer"; return PHMM_ERR_NO_DEVICE; }
+    dc.sm_count = prop.multiProcessorCount;
+    const Tables& T = host_tables();
+    CUDA_TRY(cudaMalloc(&dc.d_ph2pr_f, sizeof(float) * 128));
+    CUDA_TRY(cudaMalloc(&dc.d_mm_f, sizeof(float) * kMmEntries));
+    CUDA_TRY(cudaMalloc(&dc.d_ph2pr_d, sizeof(double) * 128));
+    CUDA_TRY(cudaMalloc(&dc.d_mm_d, sizeof(double) * kMmEntries));
+    CUDA_TRY(cudaMemcpy(dc.d_ph2pr_f, T.ph2pr_f.data(), sizeof(float) * 128, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(dc.d_mm_f, T.mm_f.data(), sizeof(float) * kMmEntries, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(dc.d_ph2pr_d, T.ph2pr_d.data(), sizeof(double) * 128, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(dc.d_mm_d, T.mm_d.data(), sizeof(double) * kMmEntries, cudaMemcpyHostToDevice));
+    dc.slots.resize(depth);
+    for (auto& s : dc.slots) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreate(&s.ev_k0));
+        CUDA_TRY(cudaEventCreate(&s.ev_k1));
+        CUDA_TRY(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+    }
+    return PHMM_OK;
+}
+
+void free_slot(Slot& s)
+{
+    s.h_in.release(); s.h_out.release(); s.h_rescue.release();
+    s.d_in.release(); s.d_out.release(); s.d_rescue.release();
+    if (s.ev_k0) cudaEventDestroy(s.ev_k0);
+    if (s.ev_k1) cudaEventDestroy(s.ev_k1);
+    if (s.ev_done) cudaEventDestroy(s.ev_done);
+    if (s.stream) cudaStreamDestroy(s.stream);
+}
+
+// contiguous split of the regions over n devices, balanced by cell count
+std::vector<int> split_regions(const phmm_batch* b, int n)
+{
+    std::vector<int> cut(n + 1, b->n_regions);
+    cut[0] = 0;
+    if (n == 1) return cut;
+    std::vector<int64_t> pre(b->n_regions + 1, 0);
+    for (int g = 0; g < b->n_regions; g++) pre[g + 1] = pre[g] + region_cells(b, g);
+    const int64_t total = pre[b->n_regions];
+    int g = 0;
+    for (int d = 1; d < n; d++) {
+        const int64_t want = total * d / n;
+        while (g < b->n_regions && pre[g + 1] <= want) g++;
+        // closer boundary of the two
+        if (g < b->n_regions && (want - pre[g]) > (pre[g + 1] - want)) g++;
+        cut[d] = std::max(cut[d - 1], g);
+    }
+    return cut;
+}
+
+}  // namespace
+
+// ---- C ABI ---------------------------------------------------------------------------------------
+
+extern "C" {
+
+int phmm_abi_version(void) { return PHMM_ABI_VERSION; }
+
+const char* phmm_strerror(int code)
+{
+    switch (code) {
+        case PHMM_OK: return "ok";
+        case PHMM_ERR_INVALID_ARG: return "invalid argument";
+        case PHMM_ERR_NO_DEVICE: return "no usable sm_100 CUDA device (this engine has no CPU fallback)";
+        case PHMM_ERR_CUDA: return "CUDA error";
+        case PHMM_ERR_OOM: return "out of memory";
+        case PHMM_ERR_UNSUPPORTED: return "unsupported input size";
+        case PHMM_ERR_BAD_TICKET: return "unknown or already waited ticket";
+        default: return "unknown error";
+    }
+}
+
+const char* phmm_last_error(const phmm_engine* e) { return e ? e->last_error.c_str() : ""; }
+
+int phmm_tables(const float** ph2pr_f32, const float** mm_f32, const double** ph2pr_f64,
+                const double** mm_f64, int32_t* mm_entries)
+{
+    const Tables& T = host_tables();
+    if (ph2pr_f32) *ph2pr_f32 = T.ph2pr_f.data();
+    if (mm_f32) *mm_f32 = T.mm_f.data();
+    if (ph2pr_f64) *ph2pr_f64 = T.ph2pr_d.data();
+    if (mm_f64) *mm_f64 = T.mm_d.data();
+    if (mm_entries) *mm_entries = kMmEntries;
+    return PHMM_OK;
+}
+
+int phmm_normalize_filter(double* lik, int32_t n_reads, int32_t n_haps, const int32_t* read_len, uint8_t* keep)
+{
+    // intel_pairhmm.hpp:24-46; constants :19-23
+    int kept = 0;
+    for (int i = 0; i < n_reads; i++) {
+        double* row = lik + (size_t)i * n_haps;
+        double best = *std::max_element(row, row + n_haps);
+        const double cap = best + (-4.5);
+        for (int j = 0; j < n_haps; j++) if (row[j] < cap) row[j] = cap;
+        const double thr = std::min(2.0, std::ceil(read_len[i] * 0.02)) * (-4.0);
+        keep[i] = (best < thr) ? 0 : 1;
+        kept += keep[i];
+    }
+    return kept;
+}
+
+int phmm_create(const phmm_options* opt, phmm_engine** out)
+{
+    if (!out) return PHMM_ERR_INVALID_ARG;
+    *out = nullptr;
+    std::unique_ptr<phmm_engine> e(new phmm_engine());
+    if (opt) std::memcpy(&e->opt, opt, std::min<size_t>(sizeof(phmm_options), opt->struct_size > 0 ? (size_t)opt->struct_size : sizeof(phmm_options)));
+    int n_dev = std::max(1, e->opt.n_devices);
+    int depth = e->opt.pipeline_depth > 0 ? e->opt.pipeline_depth : 2;
+    e->host_threads = std::max(1, e->opt.host_threads);
+    int visible = 0;
+    if (cudaGetDeviceCount(&visible) != cudaSuccess || visible == 0) return PHMM_ERR_NO_DEVICE;
+    std::string err;
+    for (int d = 0; d < n_dev; d++) {
+        std::unique_ptr<DeviceCtx> dc(new DeviceCtx());
+        dc->ordinal = (opt && opt->devices) ? opt->devices[d] : d;
+        if (dc->ordinal < 0 || dc->ordinal >= visible) return PHMM_ERR_NO_DEVICE;
+        int rc = init_device(*dc, depth, err);
+        if (rc) { fprintf(stderr, "phmm_create: %s\n", err.c_str()); return rc; }
+        e->devs.push_back(std::move(dc));
+    }
+    for (auto& dc : e->devs) { DeviceCtx* p = dc.get(); dc->worker = std::thread([p] { p->run(); }); }
+    *out = e.release();
+    return PHMM_OK;
+}
+
+void phmm_destroy(phmm_engine* e)
+{
+    if (!e) return;
+    for (auto& dc : e->devs) {
+        { std::lock_guard<std::mutex> lk(dc->mu); dc->stop = true; }
+        dc->cv.notify_all();
+        if (dc->worker.joinable()) dc->worker.join();
+        cudaSetDevice(dc->ordinal);
+        for (auto& s : dc->slots) { if (s.stream) cudaStreamSynchronize(s.stream); free_slot(s); }
+        cudaFree(dc->d_ph2pr_f); cudaFree(dc->d_mm_f); cudaFree(dc->d_ph2pr_d); cudaFree(dc->d_mm_d);
+    }
+    delete e;
+}
+
+int phmm_submit(phmm_engine* e, const phmm_batch* b, phmm_ticket* t)
+{
+    if (!e || !t) return PHMM_ERR_INVALID_ARG;
+    std::string err;
+    int rc = validate_batch(b, err);
+    if (rc) { e->set_error(err); return rc; }
+    TicketRec rec;
+    rec.t0 = std::chrono::steady_clock::now();
+    rec.n_pairs = b->n_regions ? batch_pairs(b, 0, b->n_regions) : 0;
+    const int nd = (int)e->devs.size();
+    std::vector<int> cut = b->n_regions ? split_regions(b, nd) : std::vector<int>(nd + 1, 0);
+    std::vector<int> rcs(nd, PHMM_OK);
+    std::vector<std::string> errs(nd);
+    std::vector<int> slot_of(nd, -1);
+    int active = 0;
+    for (int d = 0; d < nd; d++) {
+        if (cut[d + 1] == cut[d]) continue;
+        DeviceCtx& dc = *e->devs[d];
+        const int si = dc.next_slot;
+        if (dc.slots[si].busy) { e->set_error("all pipeline slots in flight: call phmm_wait first"); return PHMM_ERR_INVALID_ARG; }
+        slot_of[d] = si;
+        active++;
+    }
+    Latch latch(active);
+    for (int d = 0; d < nd; d++) {
+        if (slot_of[d] < 0) continue;
+        DeviceCtx& dc = *e->devs[d];
+        Slot& s = dc.slots[slot_of[d]];
+        s.busy = true;
+        dc.next_slot = (dc.next_slot + 1) % (int)dc.slots.size();
+        const int64_t out0 = batch_pairs(b, 0, cut[d]);
+        const int g0 = cut[d], g1 = cut[d + 1];
+        const bool exact = e->opt.exact_fp32 != 0;
+        dc.post([&, d, g0, g1, out0, exact] {
+            rcs[d] = stage_and_launch(*e->devs[d], e->devs[d]->slots[slot_of[d]], b, g0, g1, out0, exact, true, errs[d]);
+            latch.done();
+        });
+        rec.parts.emplace_back(d, slot_of[d]);
+    }
+    latch.wait();     // caller's arrays are copied: they may be released now
+    for (int d = 0; d < nd; d++)
+        if (rcs[d]) {
+            e->set_error(errs[d]);
+            for (auto& pr : rec.parts) e->devs[pr.first]->slots[pr.second].busy = false;
+            return rcs[d];
+        }
+    std::lock_guard<std::mutex> lk(e->mu);
+    *t = e->next_ticket++;
+    e->tickets[*t] = std::move(rec);
+    return PHMM_OK;
+}
+
+int phmm_wait(phmm_engine* e, phmm_ticket t, phmm_result* r)
+{
+    if (!e || !r) return PHMM_ERR_INVALID_ARG;
+    TicketRec rec;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        auto it = e->tickets.find(t);
+        if (it == e->tickets.end()) return PHMM_ERR_BAD_TICKET;
+        rec = std::move(it->second);
+        e->tickets.erase(it);
+    }
+    if (rec.n_pairs && !r->log10_lik) {
+        for (auto& pr : rec.parts) e->devs[pr.first]->slots[pr.second].busy = false;
+        e->set_error("result->log10_lik is NULL");
+        return PHMM_ERR_INVALID_ARG;
+    }
+    const int np = (int)rec.parts.size();
+    std::vector<int> rcs(np, PHMM_OK);
+    std::vector<std::string> errs(np);
+    Latch latch(np);
+    for (int k = 0; k < np; k++) {
+        DeviceCtx& dc = *e->devs[rec.parts[k].first];
+        Slot& s = dc.slots[rec.parts[k].second];
+        dc.post([&, k] {
+            rcs[k] = finalize_part(e, *e->devs[rec.parts[k].first], e->devs[rec.parts[k].first]->slots[rec.parts[k].second], r, errs[k]);
+            latch.done();
+        });
+        (void)s;
+    }
+    latch.wait();
+    phmm_stats st{};
+    st.n_pairs = rec.n_pairs;
+    int rc_all = PHMM_OK;
+    for (int k = 0; k < np; k++) {
+        Slot& s = e->devs[rec.parts[k].first]->slots[rec.parts[k].second];
+        const Part& p = s.part;
+        st.n_cells += p.n_cells; st.n_rescued += p.rescue_count;
+        st.h2d_bytes += (int64_t)p.h2d_bytes; st.d2h_bytes += (int64_t)p.d2h_bytes;
+        st.kernel_launches += p.launches;
+        st.kernel_ms = std::max(st.kernel_ms, p.kernel_ms);
+        st.n_devices_used++;
+        s.busy = false;
+        if (rcs[k] && !rc_all) { rc_all = rcs[k]; e->set_error(errs[k]); }
+    }
+    st.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - rec.t0).count();
+    r->stats = st;
+    return rc_all;
+}
+
+int phmm_compute(phmm_engine* e, const phmm_batch* b, phmm_result* r)
+{
+    phmm_ticket t;
+    int rc = phmm_submit(e, b, &t);
+    if (rc) return rc;
+    return phmm_wait(e, t, r);
+}
+
+// ---- device-resident form (bench: inputs already in HBM) -------------------------------------
+
+int phmm_stage(phmm_engine* e, const phmm_batch* b, phmm_staged** out)
+{
+    if (!e || !out) return PHMM_ERR_INVALID_ARG;
+    *out = nullptr;
+    std::string err;
+    int rc = validate_batch(b, err);
+    if (rc) { e->set_error(err); return rc; }
+    if (b->n_regions == 0) { e->set_error("empty batch"); return PHMM_ERR_INVALID_ARG; }
+    std::unique_ptr<phmm_staged> st(new phmm_staged());
+    DeviceCtx& dc = *e->devs[0];
+    Latch latch(1);
+    dc.post([&] {
+        Slot& s = st->slot;
+        auto go = [&]() -> int {
+            CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreate(&s.ev_k0));
+            CUDA_TRY(cudaEventCreate(&s.ev_k1));
+            CUDA_TRY(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+            int rc2 = stage_and_launch(dc, s, b, 0, b->n_regions, 0, e->opt.exact_fp32 != 0, false, err);
+            if (rc2) return rc2;
+            CUDA_TRY(cudaStreamSynchronize(s.stream));
+            return PHMM_OK;
+        };
+        rc = go();
+        latch.done();
+    });
+    latch.wait();
+    if (rc) { e->set_error(err); Latch l2(1); dc.post([&] { free_slot(st->slot); l2.done(); }); l2.wait(); return rc; }
+    *out = st.release();
+    return PHMM_OK;
+}
+
+int phmm_run_staged(phmm_engine* e, phmm_staged* st, int32_t iters, float* ms_per_iter, int32_t* launches_per_iter)
+{
+    if (!e || !st || iters < 1) return PHMM_ERR_INVALID_ARG;
+    DeviceCtx& dc = *e->devs[0];
+    std::string err;
+    int rc = PHMM_OK;
+    float ms = 0.f;
+    int launches = 0;
+    Latch latch(1);
+    dc.post([&] {
+        Slot& s = st->slot;
+        Part& p = s.part;
+        const bool exact = e->opt.exact_fp32 != 0;
+        auto go = [&]() -> int {
+            const size_t smem = sizeof(uint32_t) * (size_t)s.args.smem_words_per_warp * kWarpsPerCta;
+            CUDA_TRY(cudaEventRecord(s.ev_k0, s.stream));
+            for (int it = 0; it < iters; it++) {
+                launches = 0;
+                CUDA_TRY(cudaMemsetAsync(s.d_out.p, 0, 16, s.stream));
+                for (int f64 = 0; f64 < 2; f64++)
+                    for (int k = 0; k < kMaxRowsPerLane; k++) {
+                        const int n = p.job_beg[k + 1] - p.job_beg[k];
+                        if (n == 0) continue;
+                        KernelFn fn = kernel_table().fn[f64][exact ? 1 : 0][p.uniform ? 1 : 0][k];
+                        KernelArgs ak = s.args;
+                        ak.jobs = s.args.jobs + p.job_beg[k];
+                        ak.n_jobs = n;
+                        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        dim3 grid((n + kWarpsPerCta - 1) / kWarpsPerCta, p.hap_chunks);
+                        fn<<<grid, kWarpsPerCta * 32, smem, s.stream>>>(ak);
+                        CUDA_TRY(cudaGetLastError());
+                        launches++;
+                    }
+            }
+            CUDA_TRY(cudaEventRecord(s.ev_k1, s.stream));
+            CUDA_TRY(cudaEventSynchronize(s.ev_k1));
+            CUDA_TRY(cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1));
+            return PHMM_OK;
+        };
+        rc = go();
+        latch.done();
+    });
+    latch.wait();
+    if (rc) { e->set_error(err); return rc; }
+    st->ran = true;
+    st->slot.part.launches = launches;
+    if (ms_per_iter) *ms_per_iter = ms / iters;
+    if (launches_per_iter) *launches_per_iter = launches;
+    return PHMM_OK;
+}
+
+int phmm_fetch_staged(phmm_engine* e, phmm_staged* st, phmm_result* r)
+{
+    if (!e || !st || !r || !r->log10_lik) return PHMM_ERR_INVALID_ARG;
+    if (!st->ran) { e->set_error("phmm_run_staged has not been called"); return PHMM_ERR_INVALID_ARG; }
+    DeviceCtx& dc = *e->devs[0];
+    std::string err;
+    int rc = PHMM_OK;
+    Latch latch(1);
+    dc.post([&] {
+        Slot& s = st->slot;
+        auto go = [&]() -> int {
+            const size_t out_bytes = 16 + sizeof(float) * (size_t)s.part.n_pairs;
+            CUDA_TRY(cudaMemcpyAsync(s.h_out.p, s.d_out.p, out_bytes, cudaMemcpyDeviceToHost, s.stream));
+            CUDA_TRY(cudaEventRecord(s.ev_done, s.stream));
+            s.part.d2h_bytes = out_bytes;
+            return finalize_part(e, dc, s, r, err);
+        };
+        rc = go();
+        latch.done();
+    });
+    latch.wait();
+    if (rc) { e->set_error(err); return rc; }
+    const Part& p = st->slot.part;
+    phmm_stats stt{};
+    stt.n_pairs = p.n_pairs; stt.n_cells = p.n_cells; stt.n_rescued = p.rescue_count;
+    stt.h2d_bytes = (int64_t)p.h2d_bytes; stt.d2h_bytes = (int64_t)p.d2h_bytes;
+    stt.kernel_launches = p.launches; stt.n_devices_used = 1; stt.kernel_ms = p.kernel_ms;
+    r->stats = stt;
+    return PHMM_OK;
+}
+
+void phmm_free_staged(phmm_engine* e, phmm_staged* st)
+{
+    if (!e || !st) return;
+    DeviceCtx& dc = *e->devs[0];
+    Latch latch(1);
+    dc.post([&] { if (st->slot.stream) cudaStreamSynchronize(st->slot.stream); free_slot(st->slot); latch.done(); });
+    latch.wait();
+    delete st;
+}
+
+}  // extern "C"

@@ -1,0 +1,396 @@
+// phmm_kernels.cuh -- sm_100a PairHMM forward kernels (FP32 packed f32x2, FP64 rescue).
+//
+// Replaces the reference's per-pair AVX kernels compute_full_prob_avxs<float> /
+// compute_full_prob_avxd<double> (pairhmm/native/avx-pairhmm-template.h:210-346) and their
+// per-pair setup (initializeVectors :83-128, precompute_masks :3-35).  Not a translation: the
+// reference stripes 8 (4) rows over AVX lanes and walks anti-diagonals with lane shifts
+// (avx-vector-shift.h); here
+//
+//   * a LANE GROUP of G lanes owns one column wavefront; lane l owns K consecutive read rows whose
+//     M/X/Y state, priors and transition factors live in registers, so one step (= one haplotype
+//     column per lane) is K cell updates against 3 shuffled values (the bottom row handed to lane
+//     l+1), instead of 3 lane shifts per cell;
+//   * the FP32 kernel packs TWO reads (same haplotype) into the two halves of f32x2 registers
+//     (FFMA2/FMUL2/FADD2 on sm_100): 8 packed FP32-pipe instructions update two cells, which frees
+//     issue slots for the 2 LOP3 + 2 FSEL per cell pair that pick the match/mismatch prior
+//     (measured on B200: FFMA and FFMA2 both saturate at ~125 lane-FMAs/clk/SM, integer/select ops
+//     at 64/clk/SM -- profiles/r01_microbench_pipes.txt);
+//   * the haplotype is staged once per warp in shared memory as one 32-bit word per column holding
+//     the base's one-hot nibble replicated 8 times (A=1,C=2,T=4,G=8,N=15), the K read bases of a
+//     lane are packed as nibbles of one register, so "bases equal or either is N"
+//     (avx-pairhmm-template.h:3-35,70-75) is a single LOP3 with predicate output per cell;
+//   * reads are right-aligned in the K*G row block: missing rows at the top are DUMMY rows that
+//     reproduce row 0 of the reference (M = X = 0, Y = INITIAL_CONSTANT/haplen,
+//     avx-pairhmm-template.h:86-92,161-175) exactly (priors 0, Y self-transition 1), so the last
+//     read row is always the last row of the last lane and the final sum (:328-343) is a running
+//     sum in that lane, in the reference's column order.
+//
+// Arithmetic: default is FMA-contracted (8 FP32-pipe instructions per cell: the roofline unit of
+// SURVEY.md section 8d); EXACT=true uses unfused mul/add in the reference's operation order and
+// is bit-identical to the reference's raw results.  FP32 is flush-to-zero (intel_pairhmm.hpp:102-105).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace phmm {
+
+constexpr int kWarpsPerCta = 4;
+constexpr int kMaxJobReads = 4;          // reads per warp job: 2 per lane group, up to 2 groups
+constexpr float kMinAccepted = 1e-28f;   // pairhmm/native/pairhmm_common.h:16
+
+struct WarpJob {
+    int32_t region;
+    int32_t read[kMaxJobReads];          // global read indices, -1 = none
+};
+
+struct RescueOut {                       // one rescued pair (FP64 redo), compacted for D2H
+    int64_t out_idx;
+    double  raw64;
+};
+
+struct KernelArgs {
+    // batch (device pointers)
+    const int32_t* read_off;
+    const uint8_t* read_bases;
+    const uint8_t* read_q;
+    const uint8_t* read_i;
+    const uint8_t* read_d;
+    const uint8_t* read_c;
+    const uchar4*  read_gap;             // UNIFORM: per read (i, d, c, -) applying to every base
+    const int32_t* hap_off;
+    const uint8_t* hap_bases;
+    const int32_t* region_read_beg;
+    const int32_t* region_hap_beg;
+    const int64_t* region_out_beg;
+    // probability tables (host-built, native/Context.h semantics)
+    const float*  ph2pr_f;
+    const float*  mm_f;
+    const double* ph2pr_d;
+    const double* mm_d;
+    // work list
+    const WarpJob* jobs;
+    int32_t n_jobs;
+    int32_t haps_per_job;
+    int32_t smem_words_per_warp;
+    // results
+    float*     raw32;                    // [n_pairs]
+    RescueOut* rescue_out;               // [n_pairs] capacity
+    unsigned*  rescue_count;
+};
+
+// ---- precision policies --------------------------------------------------------------------
+
+struct PolicyF32x2 {
+    using S = float;
+    using V = float2;
+    static constexpr int NH = 2;         // reads packed per lane group
+    static constexpr bool kIsF32 = true;
+    __device__ static __forceinline__ V splat(S s) { return make_float2(s, s); }
+    __device__ static __forceinline__ S get(const V& v, int h) { return h ? v.y : v.x; }
+    __device__ static __forceinline__ void set(V& v, int h, S s) { if (h) v.y = s; else v.x = s; }
+    // Inline PTX with explicit .rn.ftz: (1) ptxas never contracts mul.rn + add.rn into an fma, which
+    // the EXACT kernels rely on (the __fmul2_rn/__fadd2_rn intrinsics DID get fused under -fmad);
+    // (2) flush-to-zero is stated in the instruction, not left to a compile flag.
+    __device__ static __forceinline__ unsigned long long u64(V a) { return *reinterpret_cast<unsigned long long*>(&a); }
+    __device__ static __forceinline__ V f2(unsigned long long a) { return *reinterpret_cast<V*>(&a); }
+    __device__ static __forceinline__ V mul(V a, V b) {
+        unsigned long long r; asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(u64(a)), "l"(u64(b))); return f2(r);
+    }
+    __device__ static __forceinline__ V add(V a, V b) {
+        unsigned long long r; asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(u64(a)), "l"(u64(b))); return f2(r);
+    }
+    __device__ static __forceinline__ V fma(V a, V b, V c) {
+        unsigned long long r; asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(u64(a)), "l"(u64(b)), "l"(u64(c))); return f2(r);
+    }
+    // add that ptxas cannot contract with a preceding packed mul: ptxas 12.9 fuses mul.rn.f32x2 +
+    // add.rn.f32x2 into FFMA2 even with -fmad=false (unlike the scalar forms), so the EXACT kernels
+    // add the two halves with scalar add.rn (FMUL2 + 2 FADD, never an FMA).
+    __device__ static __forceinline__ V addx(V a, V b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+    __device__ static __forceinline__ V sel(bool p0, bool p1, V a, V b) {
+        return make_float2(p0 ? a.x : b.x, p1 ? a.y : b.y);
+    }
+    __device__ static __forceinline__ V shfl_up(V v, int width) {
+        return make_float2(__shfl_up_sync(0xffffffffu, v.x, 1, width),
+                           __shfl_up_sync(0xffffffffu, v.y, 1, width));
+    }
+    __device__ static __forceinline__ S one() { return 1.0f; }
+    __device__ static __forceinline__ S three() { return 3.0f; }
+    __device__ static __forceinline__ S init_const() { return 1.329227995784916e+36f; }   // 2^120, Context.h:149
+    __device__ static __forceinline__ S ssub(S a, S b) { return __fsub_rn(a, b); }
+    __device__ static __forceinline__ S sdiv(S a, S b) { return __fdiv_rn(a, b); }
+    __device__ static __forceinline__ S sadd(S a, S b) { return __fadd_rn(a, b); }
+    __device__ static __forceinline__ const S* ph2pr(const KernelArgs& a) { return a.ph2pr_f; }
+    __device__ static __forceinline__ const S* mm(const KernelArgs& a) { return a.mm_f; }
+};
+
+struct PolicyF64 {
+    using S = double;
+    using V = double;
+    static constexpr int NH = 1;
+    static constexpr bool kIsF32 = false;
+    __device__ static __forceinline__ V splat(S s) { return s; }
+    __device__ static __forceinline__ S get(const V& v, int) { return v; }
+    __device__ static __forceinline__ void set(V& v, int, S s) { v = s; }
+    __device__ static __forceinline__ V mul(V a, V b) { return __dmul_rn(a, b); }
+    __device__ static __forceinline__ V add(V a, V b) { return __dadd_rn(a, b); }
+    __device__ static __forceinline__ V fma(V a, V b, V c) { return __fma_rn(a, b, c); }
+    __device__ static __forceinline__ V addx(V a, V b) { return __dadd_rn(a, b); }
+    __device__ static __forceinline__ V sel(bool p0, bool, V a, V b) { return p0 ? a : b; }
+    __device__ static __forceinline__ V shfl_up(V v, int width) { return __shfl_up_sync(0xffffffffu, v, 1, width); }
+    __device__ static __forceinline__ S one() { return 1.0; }
+    __device__ static __forceinline__ S three() { return 3.0; }
+    __device__ static __forceinline__ S init_const() { return 1.1235582092889474e+307; }   // 2^1020, Context.h:109
+    __device__ static __forceinline__ S ssub(S a, S b) { return __dsub_rn(a, b); }
+    __device__ static __forceinline__ S sdiv(S a, S b) { return __ddiv_rn(a, b); }
+    __device__ static __forceinline__ S sadd(S a, S b) { return __dadd_rn(a, b); }
+    __device__ static __forceinline__ const S* ph2pr(const KernelArgs& a) { return a.ph2pr_d; }
+    __device__ static __forceinline__ const S* mm(const KernelArgs& a) { return a.mm_d; }
+};
+
+// base byte -> one-hot nibble; everything that is not A,C,T,G,N is 'A' (pairhmm_common.h:26-44)
+__device__ __forceinline__ uint32_t base_nibble(uint8_t b) {
+    uint32_t n = 1u;
+    n = (b == 'C') ? 2u : n;
+    n = (b == 'T') ? 4u : n;
+    n = (b == 'G') ? 8u : n;
+    n = (b == 'N') ? 15u : n;
+    return n;
+}
+
+// ---- the forward kernel ----------------------------------------------------------------------
+//
+// grid.x : warp jobs (kWarpsPerCta per CTA);  grid.y : haplotype chunks of args.haps_per_job
+// One warp = 32/G lane groups.  FP32: group g scores reads job.read[2g], job.read[2g+1] together.
+// FP64 (rescue): group g redoes job.read[2g] and then job.read[2g+1], each only for the haplotypes
+// whose raw FP32 result is below 1e-28f (intel_pairhmm.hpp:137); it reads that decision straight
+// from args.raw32, so no work list is built between the two kernels.
+template <class P, int K, int G, bool UNIFORM, bool EXACT>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+forward_kernel(const KernelArgs args)
+{
+    using S = typename P::S;
+    using V = typename P::V;
+    constexpr int NH = P::NH;
+    constexpr int NG = 32 / G;
+    static_assert(K >= 1 && K <= 8, "K rows per lane: nibble-packed in one register");
+    static_assert(NG * 2 <= kMaxJobReads, "job too small for this group width");
+
+    extern __shared__ uint32_t smem[];
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int grp  = lane / G;
+    const int l    = lane % G;
+    const int job_idx = blockIdx.x * kWarpsPerCta + warp;
+    if (job_idx >= args.n_jobs) return;
+
+    const WarpJob job = args.jobs[job_idx];
+    const int hap_beg = args.region_hap_beg[job.region];
+    const int nh      = args.region_hap_beg[job.region + 1] - hap_beg;
+    const int h_first = blockIdx.y * args.haps_per_job;
+    if (h_first >= nh) return;
+    const int h_last  = min(nh, h_first + args.haps_per_job);
+    const int rd_beg  = args.region_read_beg[job.region];
+    const int64_t out_base = args.region_out_beg[job.region];
+    uint32_t* hs = smem + warp * args.smem_words_per_warp;
+
+    const S* __restrict__ ph2pr = P::ph2pr(args);
+    const S* __restrict__ mmtab = P::mm(args);
+
+    constexpr int NSUB = 2 / NH;         // FP64: the two reads of a group one after the other
+#pragma unroll 1
+    for (int sub = 0; sub < NSUB; ++sub) {
+        int  rd[NH];
+        bool valid[NH];
+#pragma unroll
+        for (int hf = 0; hf < NH; ++hf) {
+            rd[hf] = job.read[2 * grp + sub * NH + hf];
+            valid[hf] = rd[hf] >= 0;
+        }
+        if (!P::kIsF32) {
+            // rescue kernel: skip this read unless some haplotype of the chunk needs the redo
+            bool need = false;
+            if (valid[0])
+                for (int h = h_first + l; h < h_last; h += G)
+                    need |= args.raw32[out_base + (int64_t)(rd[0] - rd_beg) * nh + h] < kMinAccepted;
+            if (!__any_sync(0xffffffffu, need)) continue;
+        }
+        const bool group_live = valid[0];
+        if (!valid[0]) rd[0] = job.read[0];                 // idle group: shadow read 0, no output
+#pragma unroll
+        for (int hf = 1; hf < NH; ++hf) if (!valid[hf]) rd[hf] = rd[0];
+
+        // ---- per-row registers: priors and transition factors (avx-pairhmm-template.h:83-128) ----
+        V pr_mat[K], pr_mis[K];           // 1 - dist, dist / 3   (0 on dummy rows)
+        V pYY[K];                         // Y self-transition (1 on dummy rows); doubles as the X
+                                          // self-transition of the row when !UNIFORM (pXX == pYY,
+                                          // avx-pairhmm-template.h:117,119)
+        V pMM[UNIFORM ? 1 : K], pGAPM[UNIFORM ? 1 : K], pMX[UNIFORM ? 1 : K], pMY[UNIFORM ? 1 : K];
+        V pXXu;                           // UNIFORM: X self-transition of every row
+        V pMX0, pXX0;                     // row 0 of the lane (0 in lane 0: kills the wrapped shuffle)
+        uint32_t rnib[NH];                // K read-base nibbles
+        int pad[NH];
+#pragma unroll
+        for (int hf = 0; hf < NH; ++hf) {
+            const int r  = rd[hf];
+            const int ro = args.read_off[r];
+            const int R  = args.read_off[r + 1] - ro;
+            pad[hf] = K * G - R;          // >= 1 by construction of the plan
+            rnib[hf] = 0;
+            int gi = 0, gd = 0, gc = 0;
+            if (UNIFORM) {
+                const uchar4 gp = args.read_gap[r];
+                gi = gp.x & 127; gd = gp.y & 127; gc = gp.z & 127;
+                const int mx = max(gi, gd), mn = min(gi, gd);
+                P::set(pMM[0], hf, mmtab[((mx * (mx + 1)) >> 1) + mn]);
+                P::set(pGAPM[0], hf, P::ssub(P::one(), ph2pr[gc]));
+                P::set(pMX[0], hf, ph2pr[gi]);
+                P::set(pMY[0], hf, ph2pr[gd]);
+                P::set(pXXu, hf, ph2pr[gc]);
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int ri = l * K + k - pad[hf];
+                S mat = 0, mis = 0, yy = P::one();
+                S mm_ = 0, gapm = 0, mx_ = 0, my_ = 0;
+                uint32_t nib = 0;
+                if (ri >= 0) {
+                    nib = base_nibble(args.read_bases[ro + ri]);
+                    const S dist = ph2pr[args.read_q[ro + ri] & 127];
+                    mat = P::ssub(P::one(), dist);
+                    mis = P::sdiv(dist, P::three());
+                    if (!UNIFORM) {
+                        gi = args.read_i[ro + ri] & 127;
+                        gd = args.read_d[ro + ri] & 127;
+                        gc = args.read_c[ro + ri] & 127;
+                        const int mx = max(gi, gd), mn = min(gi, gd);
+                        mm_  = mmtab[((mx * (mx + 1)) >> 1) + mn];
+                        gapm = P::ssub(P::one(), ph2pr[gc]);
+                        mx_  = ph2pr[gi];
+                        my_  = ph2pr[gd];
+                        yy   = ph2pr[gc];
+                    } else {
+                        yy = P::get(pXXu, hf);
+                    }
+                }
+                rnib[hf] |= nib << (4 * k);
+                P::set(pr_mat[k], hf, mat);
+                P::set(pr_mis[k], hf, mis);
+                P::set(pYY[k], hf, yy);
+                if (!UNIFORM) {
+                    P::set(pMM[k], hf, mm_);
+                    P::set(pGAPM[k], hf, gapm);
+                    P::set(pMX[k], hf, mx_);
+                    P::set(pMY[k], hf, my_);
+                }
+            }
+        }
+        if (!UNIFORM) pXXu = P::splat(0);
+        pMX0 = (l == 0) ? P::splat(0) : pMX[0];
+        pXX0 = (l == 0) ? P::splat(0) : (UNIFORM ? pXXu : pYY[0]);
+
+        // ---- haplotypes of this chunk ----
+#pragma unroll 1
+        for (int h = h_first; h < h_last; ++h) {
+            int64_t out_idx[NH];
+            bool want[NH];
+#pragma unroll
+            for (int hf = 0; hf < NH; ++hf) {
+                out_idx[hf] = out_base + (int64_t)(rd[hf] - rd_beg) * nh + h;
+                want[hf] = valid[hf] && group_live;
+            }
+            if (!P::kIsF32) {
+                want[0] = want[0] && (args.raw32[out_idx[0]] < kMinAccepted);
+                if (!__any_sync(0xffffffffu, want[0])) continue;
+            }
+            const int ho = args.hap_off[hap_beg + h];
+            const int H  = args.hap_off[hap_beg + h + 1] - ho;
+
+            // stage: one replicated-nibble word per haplotype column
+            __syncwarp();
+            for (int j = lane; j < H; j += 32)
+                hs[j] = base_nibble(args.hap_bases[ho + j]) * 0x11111111u;
+            __syncwarp();
+
+            // column-0 state (avx-pairhmm-template.h:161-175): M = X = 0; Y = init_Y on row 0
+            const S init_y = P::sdiv(P::init_const(), (S)H);
+            V M[K], X[K], Y[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                M[k] = P::splat(0); X[k] = P::splat(0);
+#pragma unroll
+                for (int hf = 0; hf < NH; ++hf)
+                    P::set(Y[k], hf, (l * K + k < pad[hf]) ? init_y : (S)0);
+            }
+            // values of the row above this lane's first row: at the current column (in*) and at
+            // the previous column (dg*).  Lane 0 never uses them (its row 0 is a dummy row with
+            // zero priors, pMX0 = pXX0 = 0 and pYY = 1).
+            V inM = P::splat(0), inX = P::splat(0), inY = P::shfl_up(Y[K - 1], G);
+            V dgM = inM, dgX = inX, dgY = inY;
+            V sumM = P::splat(0), sumX = P::splat(0);
+
+            const int steps = H + G - 1;
+            const uint32_t* hp = hs - l - 1;                // hp[t] = word of column t - l
+#pragma unroll 2
+            for (int t = 1; t <= steps; ++t) {
+                const int c = t - l;                        // this lane's column, 1-based
+                if ((unsigned)(c - 1) < (unsigned)H) {
+                    const uint32_t hw = hp[t];
+                    V dM = dgM, dX = dgX, dY = dgY;         // (row-1, c-1)
+                    V uM = inM, uX = inX;                   // (row-1, c)
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const int kk = UNIFORM ? 0 : k;
+                        const uint32_t field = 0xFu << (4 * k);
+                        const bool m0 = (rnib[0] & hw & field) != 0;
+                        const bool m1 = (NH > 1) ? ((rnib[NH - 1] & hw & field) != 0) : false;
+                        const V prior = P::sel(m0, m1, pr_mat[k], pr_mis[k]);
+                        const V cMX = (k == 0) ? pMX0 : pMX[kk];
+                        const V cXX = (k == 0) ? pXX0 : (UNIFORM ? pXXu : pYY[k]);
+                        V nM, nX, nY;
+                        if (EXACT) {
+                            // reference operation order, unfused (avx-pairhmm-template.h:188,194,197)
+                            V t0 = P::addx(P::addx(P::mul(dM, pMM[kk]), P::mul(dX, pGAPM[kk])), P::mul(dY, pGAPM[kk]));
+                            nM = P::mul(t0, prior);
+                            nX = P::addx(P::mul(uM, cMX), P::mul(uX, cXX));
+                            nY = P::addx(P::mul(M[k], pMY[kk]), P::mul(Y[k], pYY[k]));
+                        } else {
+                            V t0 = P::mul(dM, pMM[kk]);
+                            t0 = P::fma(dX, pGAPM[kk], t0);
+                            t0 = P::fma(dY, pGAPM[kk], t0);
+                            nM = P::mul(t0, prior);
+                            nX = P::fma(uX, cXX, P::mul(uM, cMX));
+                            nY = P::fma(Y[k], pYY[k], P::mul(M[k], pMY[kk]));
+                        }
+                        dM = M[k]; dX = X[k]; dY = Y[k];
+                        uM = nM;   uX = nX;
+                        M[k] = nM; X[k] = nX; Y[k] = nY;
+                    }
+                    // last row of the last lane is the last read row: running sums (:328-343)
+                    sumM = EXACT ? P::addx(sumM, M[K - 1]) : P::add(sumM, M[K - 1]);
+                    sumX = EXACT ? P::addx(sumX, X[K - 1]) : P::add(sumX, X[K - 1]);
+                }
+                dgM = inM; dgX = inX; dgY = inY;
+                inM = P::shfl_up(M[K - 1], G);
+                inX = P::shfl_up(X[K - 1], G);
+                inY = P::shfl_up(Y[K - 1], G);
+            }
+
+            if (l == G - 1) {
+#pragma unroll
+                for (int hf = 0; hf < NH; ++hf) {
+                    if (!want[hf]) continue;
+                    const S res = P::sadd(P::get(sumM, hf), P::get(sumX, hf));
+                    if (P::kIsF32) {
+                        args.raw32[out_idx[hf]] = (float)res;
+                    } else {
+                        const unsigned slot = atomicAdd(args.rescue_count, 1u);
+                        args.rescue_out[slot].out_idx = out_idx[hf];
+                        args.rescue_out[slot].raw64 = (double)res;
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace phmm

@@ -1,0 +1,156 @@
+/*
+ * phmm.h -- C ABI of the B200-native PairHMM forward engine (libphmm_b200.so).
+ *
+ * This is the drop-in boundary for ONE path of avis9ditiu/gatk-haplotypecaller-cpp17: the
+ * read x haplotype log10-likelihood step.  Reference citations are relative to
+ * /root/reference/src/haplotypecaller/.
+ *
+ * What each entry point replaces in the reference:
+ *   phmm_create / phmm_destroy   hc::IntelPairHMM construction + initNative()
+ *                                (pairhmm/intel_pairhmm.hpp:16, :77-113): table build
+ *                                (native/Context.h:101-115,141-155), base-code table
+ *                                (native/pairhmm_common.h:26-44).  Here: once per process,
+ *                                not once per region (haplotypecaller.hpp:90).
+ *   phmm_batch                   getData()'s testcase[read][hap] pointer grid
+ *                                (intel_pairhmm.hpp:154-203, native/pairhmm_common.h:20-24),
+ *                                laid out as the SoA form of the accelerator batch the reference
+ *                                declares but never calls (native/shacc_pairhmm.h:12-35), and
+ *                                widened to many regions per batch.
+ *   phmm_compute                 computeLikelihoodsNative() (intel_pairhmm.hpp:115-152): FP32
+ *                                forward per pair, FP64 redo iff raw < 1e-28f, log10 minus the
+ *                                scaling constant.  The kernels replace compute_full_prob_avxs /
+ *                                compute_full_prob_avxd (native/avx-pairhmm-template.h:210-346).
+ *   phmm_submit / phmm_wait      no reference analogue (its window loop is serial,
+ *                                haplotypecaller.hpp:138-152): asynchronous form of phmm_compute
+ *                                so batch N+1 uploads while batch N computes.
+ *   phmm_normalize_filter        normalize_likelihoods_and_filter_poorly_modeled_reads()
+ *                                (intel_pairhmm.hpp:24-46), host-side, unchanged semantics.
+ *
+ * Semantics that are deliberately the reference's:
+ *   - quality, gap-open and gap-continuation bytes are consumed RAW (ASCII, & 127), no Phred+33
+ *     subtraction (native/avx-pairhmm-template.h:110-112,125);
+ *   - bases map A,C,T,G,N -> codes, every other byte (incl. lower case) -> 'A'
+ *     (native/pairhmm_common.h:26-44); N on either side matches;
+ *   - FP32 with flush-to-zero, result scaled by 2^120; FP64 scaled by 2^1020.
+ *
+ * There is no CPU fallback: every compute entry point fails with PHMM_ERR_CUDA /
+ * PHMM_ERR_NO_DEVICE when no sm_100 device is usable.
+ */
+#ifndef PHMM_H
+#define PHMM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHMM_ABI_VERSION 1
+
+/* status codes (reference has none on this path: bad input there is UB) */
+enum {
+    PHMM_OK              = 0,
+    PHMM_ERR_INVALID_ARG = 1,
+    PHMM_ERR_NO_DEVICE   = 2,
+    PHMM_ERR_CUDA        = 3,
+    PHMM_ERR_OOM         = 4,
+    PHMM_ERR_UNSUPPORTED = 5,   /* e.g. read longer than PHMM_MAX_READ_LEN */
+    PHMM_ERR_BAD_TICKET  = 6
+};
+
+#define PHMM_MAX_READ_LEN 2040    /* rows; 8 passes of 255 rows per lane group                 */
+#define PHMM_MAX_HAP_LEN  8192    /* columns staged in shared memory per lane group            */
+
+typedef struct phmm_engine phmm_engine;
+typedef int64_t phmm_ticket;
+
+typedef struct phmm_options {
+    int32_t struct_size;        /* sizeof(phmm_options), for forward compatibility             */
+    int32_t n_devices;          /* 0 or 1: one device; >1: shard regions over devices[]        */
+    const int32_t* devices;     /* CUDA ordinals; NULL = 0..n_devices-1                        */
+    int32_t pipeline_depth;     /* in-flight batches per device (streams + buffers); 0 = 2     */
+    int32_t exact_fp32;         /* 1: unfused mul/add, raw FP32 bit-identical to the reference */
+    int32_t host_threads;       /* threads for the log10 finalize step; 0 = 1                  */
+    int32_t reserved[3];
+} phmm_options;
+
+/*
+ * One batch = many active regions; every read of a region is scored against every haplotype of
+ * that region.  All arrays are caller-owned and may be released after phmm_submit returns.
+ *   region g: reads  [region_read_beg[g], region_read_beg[g+1])
+ *             haps   [region_hap_beg[g],  region_hap_beg[g+1])
+ *   read r:   bytes  [read_off[r], read_off[r+1]) of read_bases/read_q/read_i/read_d/read_c
+ *   hap h:    bytes  [hap_off[h], hap_off[h+1]) of hap_bases
+ * read_i/read_d/read_c may all three be NULL: then gap_open_i/gap_open_d/gap_cont_c apply to
+ * every base (the reference's constant 'I' / 'I' / '+' strings, sam/sam.hpp:30-32,47-49).
+ * Output order: region g occupies a row-major [reads_g][haps_g] block starting at
+ * sum_{g'<g} reads_g' * haps_g'.
+ */
+typedef struct phmm_batch {
+    int32_t n_regions, n_reads, n_haps;
+    const int32_t* region_read_beg;   /* [n_regions+1] */
+    const int32_t* region_hap_beg;    /* [n_regions+1] */
+    const int32_t* read_off;          /* [n_reads+1]   */
+    const uint8_t* read_bases;
+    const uint8_t* read_q;
+    const uint8_t* read_i;            /* insertion gap-open, per base, or NULL */
+    const uint8_t* read_d;            /* deletion gap-open, per base, or NULL  */
+    const uint8_t* read_c;            /* gap continuation, per base, or NULL   */
+    const int32_t* hap_off;           /* [n_haps+1]    */
+    const uint8_t* hap_bases;
+    uint8_t gap_open_i, gap_open_d, gap_cont_c, reserved0;   /* used when read_i == NULL */
+} phmm_batch;
+
+typedef struct phmm_stats {
+    int64_t n_pairs, n_cells, n_rescued;
+    int64_t h2d_bytes, d2h_bytes;
+    int32_t kernel_launches;
+    int32_t n_devices_used;
+    float   kernel_ms;      /* device time of the forward kernels (CUDA events), max over devices */
+    float   total_ms;       /* host wall time submit -> results written                          */
+} phmm_stats;
+
+typedef struct phmm_result {
+    double*  log10_lik;     /* [n_pairs] required: final log10 likelihoods (pre cap/filter)     */
+    float*   raw32;         /* [n_pairs] optional: raw FP32 forward sums (scaled by 2^120)      */
+    double*  raw64;         /* [n_pairs] optional: raw FP64 sums of rescued pairs, 0 elsewhere  */
+    uint8_t* rescued;       /* [n_pairs] optional: 1 where the FP64 redo was taken              */
+    phmm_stats stats;       /* out */
+} phmm_result;
+
+int  phmm_create(const phmm_options* opt, phmm_engine** out);
+void phmm_destroy(phmm_engine* e);
+int  phmm_compute(phmm_engine* e, const phmm_batch* b, phmm_result* r);
+int  phmm_submit(phmm_engine* e, const phmm_batch* b, phmm_ticket* t);
+int  phmm_wait(phmm_engine* e, phmm_ticket t, phmm_result* r);
+const char* phmm_strerror(int code);
+const char* phmm_last_error(const phmm_engine* e);
+int  phmm_abi_version(void);
+
+/* Host-side cap + filter of one region's matrix, in place (intel_pairhmm.hpp:24-46).
+ * keep[r] = 0 for reads to erase; returns the number kept.  Rows are not compacted. */
+int  phmm_normalize_filter(double* lik, int32_t n_reads, int32_t n_haps,
+                           const int32_t* read_len, uint8_t* keep);
+
+/* Read-only views of the host-built probability tables (native/Context.h:17-24), for tests. */
+int  phmm_tables(const float** ph2pr_f32, const float** mm_f32,
+                 const double** ph2pr_f64, const double** mm_f64, int32_t* mm_entries);
+
+/*
+ * Device-resident form, used by bench.py for the "inputs already in HBM" number:
+ * phmm_stage uploads and plans once, phmm_run_staged launches the forward + rescue kernels
+ * `iters` times back to back and returns the mean device time per iteration (CUDA events on the
+ * launching stream), phmm_fetch_staged brings the results of the last run back.
+ */
+typedef struct phmm_staged phmm_staged;
+int  phmm_stage(phmm_engine* e, const phmm_batch* b, phmm_staged** out);
+int  phmm_run_staged(phmm_engine* e, phmm_staged* s, int32_t iters, float* ms_per_iter,
+                     int32_t* launches_per_iter);
+int  phmm_fetch_staged(phmm_engine* e, phmm_staged* s, phmm_result* r);
+void phmm_free_staged(phmm_engine* e, phmm_staged* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHMM_H */
