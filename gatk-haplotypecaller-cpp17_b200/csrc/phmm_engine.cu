@@ -42,8 +42,8 @@ constexpr size_t kAlign = 256;
 inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 
 struct KernelTable {
-    // [f64][exact][uniform][K-1]
-    KernelFn fn[2][2][2][kMaxRowsPerLane];
+    // [f64][exact][mode][K-1]
+    KernelFn fn[2][2][3][kMaxRowsPerLane];
     KernelTable() {
         register_f32_fast(fn[0][0]);
         register_f32_exact(fn[0][1]);
@@ -92,7 +92,8 @@ struct Part {
     int g0 = 0, g1 = 0;                       // region range in the caller's batch
     int n_regions = 0, n_reads = 0, n_haps = 0;
     int64_t n_pairs = 0, n_cells = 0, out0 = 0;   // out0: offset of this part in the batch output
-    bool uniform = true;
+    int mode = kModeGeneral;                 // kernel MODE: general / batch-constant gaps / constant with i == d
+    uint8_t gap[3] = {0, 0, 0};              // the batch-constant (i, d, c) bytes when mode != general
     int max_H = 0, max_nh = 0;
     int n_jobs = 0;
     int job_beg[kMaxRowsPerLane + 1] = {0};
@@ -261,20 +262,20 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
     const int hb0 = b->hap_off[h0], hb1 = b->hap_off[h1];
     const size_t read_bytes = (size_t)(rb1 - rb0), hap_bytes = (size_t)(hb1 - hb0);
 
-    // uniform gap penalties? (always, for the reference's own callers: sam/sam.hpp:30-32)
-    std::vector<uchar4> gap(p.n_reads);
-    p.uniform = true;
+    // Batch-constant gap penalties?  Always, for the reference's own callers (sam/sam.hpp:30-32);
+    // per-base arrays are scanned once here, and the general kernels run only if they really vary.
+    bool constant = true;
     if (!b->read_i) {
-        for (auto& gq : gap) gq = make_uchar4(b->gap_open_i, b->gap_open_d, b->gap_cont_c, 0);
+        p.gap[0] = b->gap_open_i; p.gap[1] = b->gap_open_d; p.gap[2] = b->gap_cont_c;
     } else {
-        for (int r = r0; r < r1 && p.uniform; r++) {
-            const int o = b->read_off[r], R = b->read_off[r + 1] - o;
-            const uint8_t i0 = b->read_i[o], d0 = b->read_d[o], c0 = b->read_c[o];
-            for (int k = 1; k < R; k++)
-                if (b->read_i[o + k] != i0 || b->read_d[o + k] != d0 || b->read_c[o + k] != c0) { p.uniform = false; break; }
-            gap[r - r0] = make_uchar4(i0, d0, c0, 0);
-        }
+        p.gap[0] = b->read_i[rb0]; p.gap[1] = b->read_d[rb0]; p.gap[2] = b->read_c[rb0];
+        const uint8_t* end;
+        end = b->read_i + rb1; for (const uint8_t* q = b->read_i + rb0; q < end && constant; ++q) constant = (*q == p.gap[0]);
+        end = b->read_d + rb1; for (const uint8_t* q = b->read_d + rb0; q < end && constant; ++q) constant = (*q == p.gap[1]);
+        end = b->read_c + rb1; for (const uint8_t* q = b->read_c + rb0; q < end && constant; ++q) constant = (*q == p.gap[2]);
     }
+    p.mode = !constant ? kModeGeneral : (((p.gap[0] & 127) == (p.gap[1] & 127)) ? kModeConstShared : kModeConst);
+    const bool general = p.mode == kModeGeneral;
 
     // ---- plan: per region, reads of equal K are scored two at a time ----
     std::vector<WarpJob> jobs_k[kMaxRowsPerLane];
@@ -321,10 +322,9 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
     const size_t o_reg_out  = take(sizeof(int64_t) * (p.n_regions + 1));
     const size_t o_bases    = take(read_bytes);
     const size_t o_q        = take(read_bytes);
-    const size_t o_gi       = p.uniform ? 0 : take(read_bytes);
-    const size_t o_gd       = p.uniform ? 0 : take(read_bytes);
-    const size_t o_gc       = p.uniform ? 0 : take(read_bytes);
-    const size_t o_gap      = p.uniform ? take(sizeof(uchar4) * p.n_reads) : 0;
+    const size_t o_gi       = general ? take(read_bytes) : 0;
+    const size_t o_gd       = general ? take(read_bytes) : 0;
+    const size_t o_gc       = general ? take(read_bytes) : 0;
     const size_t o_haps     = take(hap_bytes);
     const size_t o_jobs     = take(sizeof(WarpJob) * p.n_jobs);
     const size_t in_bytes   = off;
@@ -356,12 +356,10 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
         }
         std::memcpy(hp + o_bases, b->read_bases + rb0, read_bytes);
         std::memcpy(hp + o_q, b->read_q + rb0, read_bytes);
-        if (!p.uniform) {
+        if (general) {
             std::memcpy(hp + o_gi, b->read_i + rb0, read_bytes);
             std::memcpy(hp + o_gd, b->read_d + rb0, read_bytes);
             std::memcpy(hp + o_gc, b->read_c + rb0, read_bytes);
-        } else {
-            std::memcpy(hp + o_gap, gap.data(), sizeof(uchar4) * p.n_reads);
         }
         std::memcpy(hp + o_haps, b->hap_bases + hb0, hap_bytes);
         WarpJob* jd = (WarpJob*)(hp + o_jobs);
@@ -378,16 +376,26 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
     a.region_out_beg = (const int64_t*)(dp + o_reg_out);
     a.read_bases = dp + o_bases;
     a.read_q = dp + o_q;
-    a.read_i = p.uniform ? nullptr : dp + o_gi;
-    a.read_d = p.uniform ? nullptr : dp + o_gd;
-    a.read_c = p.uniform ? nullptr : dp + o_gc;
-    a.read_gap = p.uniform ? (const uchar4*)(dp + o_gap) : nullptr;
+    a.read_i = general ? dp + o_gi : nullptr;
+    a.read_d = general ? dp + o_gd : nullptr;
+    a.read_c = general ? dp + o_gc : nullptr;
+    if (!general) {
+        // transition factors of the one (i,d,c) triple (avx-pairhmm-template.h:114-119), per precision
+        const Tables& T = host_tables();
+        const int gi = p.gap[0] & 127, gd = p.gap[1] & 127, gc = p.gap[2] & 127;
+        const int mx = std::max(gi, gd), mn = std::min(gi, gd);
+        const int mmi = ((mx * (mx + 1)) >> 1) + mn;
+        a.cg_f[0] = T.mm_f[mmi]; a.cg_f[1] = 1.0f - T.ph2pr_f[gc]; a.cg_f[2] = T.ph2pr_f[gi];
+        a.cg_f[3] = T.ph2pr_f[gd]; a.cg_f[4] = T.ph2pr_f[gc];
+        a.cg_d[0] = T.mm_d[mmi]; a.cg_d[1] = 1.0 - T.ph2pr_d[gc]; a.cg_d[2] = T.ph2pr_d[gi];
+        a.cg_d[3] = T.ph2pr_d[gd]; a.cg_d[4] = T.ph2pr_d[gc];
+    }
     a.hap_bases = dp + o_haps;
     a.ph2pr_f = dc.d_ph2pr_f; a.mm_f = dc.d_mm_f; a.ph2pr_d = dc.d_ph2pr_d; a.mm_d = dc.d_mm_d;
     a.jobs = (const WarpJob*)(dp + o_jobs);
     a.n_jobs = 0;
     a.haps_per_job = p.haps_per_job;
-    a.smem_words_per_warp = (p.max_H + 31) / 32 * 32 + 32;
+    a.smem_words_per_warp = (p.max_H + 31) / 32 * 32 + 2 * kGroupWidth + 32;   // slack: see staging in the kernel
     a.rescue_count = (unsigned*)s.d_out.p;
     a.raw32 = (float*)((uint8_t*)s.d_out.p + 16);
     a.rescue_out = (RescueOut*)s.d_rescue.p;
@@ -401,7 +409,7 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
         for (int k = 0; k < kMaxRowsPerLane; k++) {
             const int n = p.job_beg[k + 1] - p.job_beg[k];
             if (n == 0) continue;
-            KernelFn fn = kernel_table().fn[f64 ? 1 : 0][exact ? 1 : 0][p.uniform ? 1 : 0][k];
+            KernelFn fn = kernel_table().fn[f64 ? 1 : 0][exact ? 1 : 0][p.mode][k];
             KernelArgs ak = a;
             ak.jobs = a.jobs + p.job_beg[k];
             ak.n_jobs = n;
@@ -802,7 +810,7 @@ int phmm_run_staged(phmm_engine* e, phmm_staged* st, int32_t iters, float* ms_pe
                     for (int k = 0; k < kMaxRowsPerLane; k++) {
                         const int n = p.job_beg[k + 1] - p.job_beg[k];
                         if (n == 0) continue;
-                        KernelFn fn = kernel_table().fn[f64][exact ? 1 : 0][p.uniform ? 1 : 0][k];
+                        KernelFn fn = kernel_table().fn[f64][exact ? 1 : 0][p.mode][k];
                         KernelArgs ak = s.args;
                         ak.jobs = s.args.jobs + p.job_beg[k];
                         ak.n_jobs = n;

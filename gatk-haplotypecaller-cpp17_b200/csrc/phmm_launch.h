@@ -15,25 +15,23 @@ void register_f32_exact(KernelFn (*tab)[kMaxRowsPerLane]);
 void register_f64_fast(KernelFn (*tab)[kMaxRowsPerLane]);
 void register_f64_exact(KernelFn (*tab)[kMaxRowsPerLane]);
 
-// tab[uniform][K-1]
+// tab[mode][K-1]   (mode: 0 general per-base gaps, 1 batch-constant gaps, 2 constant with i == d)
+#define PHMM_REGISTER_MODE(POLICY, EXACT, MODE)                                                  \
+    do {                                                                                         \
+        tab[MODE][0] = forward_kernel<POLICY, 1, kGroupWidth, MODE, EXACT>;                      \
+        tab[MODE][1] = forward_kernel<POLICY, 2, kGroupWidth, MODE, EXACT>;                      \
+        tab[MODE][2] = forward_kernel<POLICY, 3, kGroupWidth, MODE, EXACT>;                      \
+        tab[MODE][3] = forward_kernel<POLICY, 4, kGroupWidth, MODE, EXACT>;                      \
+        tab[MODE][4] = forward_kernel<POLICY, 5, kGroupWidth, MODE, EXACT>;                      \
+        tab[MODE][5] = forward_kernel<POLICY, 6, kGroupWidth, MODE, EXACT>;                      \
+        tab[MODE][6] = forward_kernel<POLICY, 7, kGroupWidth, MODE, EXACT>;                      \
+        tab[MODE][7] = forward_kernel<POLICY, 8, kGroupWidth, MODE, EXACT>;                      \
+    } while (0)
 #define PHMM_REGISTER_ALL(POLICY, EXACT)                                                         \
     do {                                                                                         \
-        tab[0][0] = forward_kernel<POLICY, 1, kGroupWidth, false, EXACT>;                        \
-        tab[0][1] = forward_kernel<POLICY, 2, kGroupWidth, false, EXACT>;                        \
-        tab[0][2] = forward_kernel<POLICY, 3, kGroupWidth, false, EXACT>;                        \
-        tab[0][3] = forward_kernel<POLICY, 4, kGroupWidth, false, EXACT>;                        \
-        tab[0][4] = forward_kernel<POLICY, 5, kGroupWidth, false, EXACT>;                        \
-        tab[0][5] = forward_kernel<POLICY, 6, kGroupWidth, false, EXACT>;                        \
-        tab[0][6] = forward_kernel<POLICY, 7, kGroupWidth, false, EXACT>;                        \
-        tab[0][7] = forward_kernel<POLICY, 8, kGroupWidth, false, EXACT>;                        \
-        tab[1][0] = forward_kernel<POLICY, 1, kGroupWidth, true, EXACT>;                         \
-        tab[1][1] = forward_kernel<POLICY, 2, kGroupWidth, true, EXACT>;                         \
-        tab[1][2] = forward_kernel<POLICY, 3, kGroupWidth, true, EXACT>;                         \
-        tab[1][3] = forward_kernel<POLICY, 4, kGroupWidth, true, EXACT>;                         \
-        tab[1][4] = forward_kernel<POLICY, 5, kGroupWidth, true, EXACT>;                         \
-        tab[1][5] = forward_kernel<POLICY, 6, kGroupWidth, true, EXACT>;                         \
-        tab[1][6] = forward_kernel<POLICY, 7, kGroupWidth, true, EXACT>;                         \
-        tab[1][7] = forward_kernel<POLICY, 8, kGroupWidth, true, EXACT>;                         \
+        PHMM_REGISTER_MODE(POLICY, EXACT, 0);                                                    \
+        PHMM_REGISTER_MODE(POLICY, EXACT, 1);                                                    \
+        PHMM_REGISTER_MODE(POLICY, EXACT, 2);                                                    \
     } while (0)
 
 }  // namespace phmm

@@ -150,6 +150,76 @@ __global__ void k_ffma_alu(Out* out, int iters, float seed) {
     EPILOGUE
 }
 
+// FFMA2 with three DISTINCT per-thread register-pair operands (register-bank pressure test)
+__global__ void k_ffma2_3r(Out* out, int iters, float seed) {
+    PROLOGUE2
+    unsigned long long bb[NCHAIN], cc[NCHAIN];
+#pragma unroll
+    for (int i = 0; i < NCHAIN; ++i) {
+        float2 f = make_float2(0.999f - 1e-3f * (threadIdx.x & 7) - 1e-4f * i, 0.998f - 1e-4f * i);
+        float2 g = make_float2(1e-3f * i + threadIdx.x * 1e-5f, 2e-3f * i);
+        bb[i] = *reinterpret_cast<unsigned long long*>(&f); cc[i] = *reinterpret_cast<unsigned long long*>(&g);
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < NCHAIN; ++i)
+            asm volatile("fma.rn.ftz.f32x2 %0, %0, %1, %2;" : "+l"(a[i]) : "l"(bb[i]), "l"(cc[i]));
+    }
+    (void)b; (void)c;
+    EPILOGUE2
+}
+// FFMA2 d = a * b + c with a, c distinct per-thread pairs and b distinct too, d != a (4 distinct pairs)
+__global__ void k_ffma2_4r(Out* out, int iters, float seed) {
+    PROLOGUE2
+    unsigned long long bb[NCHAIN], cc[NCHAIN], dd[NCHAIN];
+#pragma unroll
+    for (int i = 0; i < NCHAIN; ++i) {
+        float2 f = make_float2(0.999f - 1e-3f * (threadIdx.x & 7) - 1e-4f * i, 0.998f - 1e-4f * i);
+        float2 g = make_float2(1e-3f * i + threadIdx.x * 1e-5f, 2e-3f * i);
+        bb[i] = *reinterpret_cast<unsigned long long*>(&f); cc[i] = *reinterpret_cast<unsigned long long*>(&g); dd[i] = 0;
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < NCHAIN; ++i) {
+            asm volatile("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(dd[i]) : "l"(a[i]), "l"(bb[i]), "l"(cc[i]));
+            asm volatile("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(a[i]) : "l"(dd[i]), "l"(bb[(i + 1) % NCHAIN]));
+        }
+    }
+    (void)b; (void)c;
+    EPILOGUE2
+}
+// FMUL2 with two distinct per-thread operands
+__global__ void k_fmul2_2r(Out* out, int iters, float seed) {
+    PROLOGUE2
+    unsigned long long bb[NCHAIN];
+#pragma unroll
+    for (int i = 0; i < NCHAIN; ++i) {
+        float2 f = make_float2(0.999f - 1e-3f * (threadIdx.x & 7) - 1e-4f * i, 0.998f - 1e-4f * i);
+        bb[i] = *reinterpret_cast<unsigned long long*>(&f);
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < NCHAIN; ++i)
+            asm volatile("mul.rn.ftz.f32x2 %0, %0, %1;" : "+l"(a[i]) : "l"(bb[i]));
+    }
+    (void)b; (void)c;
+    EPILOGUE2
+}
+// scalar FFMA with three distinct per-thread operands
+__global__ void k_ffma_3r(Out* out, int iters, float seed) {
+    PROLOGUE
+    float bb[NCHAIN], cc[NCHAIN];
+#pragma unroll
+    for (int i = 0; i < NCHAIN; ++i) { bb[i] = 0.999f - 1e-3f * (threadIdx.x & 7) - 1e-4f * i; cc[i] = 1e-3f * i + threadIdx.x * 1e-5f; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < NCHAIN; ++i)
+            asm volatile("fma.rn.ftz.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(bb[i]), "f"(cc[i]));
+    }
+    (void)b; (void)c;
+    EPILOGUE
+}
+
 // shuffles only
 __global__ void k_shfl(Out* out, int iters, float seed) {
     PROLOGUE
@@ -260,6 +330,10 @@ int main(int argc, char** argv) {
         run("ffma (3-reg)", k_ffma, NCHAIN, threads, cps, sms, iters);
         run("fmul", k_fmul, NCHAIN, threads, cps, sms, iters);
         run("ffma2 (f32x2)", k_ffma2, NCHAIN, threads, cps, sms, iters);
+        run("ffma2 3 distinct reg pairs", k_ffma2_3r, NCHAIN, threads, cps, sms, iters);
+        run("ffma2(4 distinct)+fmul2", k_ffma2_4r, 2 * NCHAIN, threads, cps, sms, iters);
+        run("fmul2 2 distinct reg pairs", k_fmul2_2r, NCHAIN, threads, cps, sms, iters);
+        run("ffma 3 distinct regs", k_ffma_3r, NCHAIN, threads, cps, sms, iters);
         run("fmul2", k_fmul2, NCHAIN, threads, cps, sms, iters);
         run("fadd2", k_fadd2, NCHAIN, threads, cps, sms, iters);
         run("8 ffma2 + 2x(lop,setp,sel)", k_ffma2_alu<2>, NCHAIN, threads, cps, sms, iters);
