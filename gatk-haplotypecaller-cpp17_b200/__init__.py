@@ -16,7 +16,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libphmm_b200.so")
+LIB_PATH = os.environ.get("PHMM_LIB", os.path.join(_HERE, "libphmm_b200.so"))   # PHMM_LIB: A/B builds while tuning
 CSRC = os.path.join(_HERE, "csrc")
 
 PHMM_OK = 0

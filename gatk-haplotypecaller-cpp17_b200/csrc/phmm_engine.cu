@@ -42,8 +42,8 @@ constexpr size_t kAlign = 256;
 inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 
 struct KernelTable {
-    // [f64][exact][mode][K-1]
-    KernelFn fn[2][2][3][kMaxRowsPerLane];
+    // [f64][exact] -> [mode][shape]
+    KernelTab fn[2][2];
     KernelTable() {
         register_f32_fast(fn[0][0]);
         register_f32_exact(fn[0][1]);
@@ -53,9 +53,26 @@ struct KernelTable {
 };
 const KernelTable& kernel_table() { static KernelTable t; return t; }
 
-// rows per lane for a read of R bases: K*G >= R + 1 (at least one dummy row on top)
-inline int rows_per_lane(int R) { return (R + 1 + kGroupWidth - 1) / kGroupWidth; }
-constexpr int kMaxReadLenCompiled = kMaxRowsPerLane * kGroupWidth - 1;   // 255
+// Shape for a read of R bases against haplotypes of about H bases.  Feasible: K*G >= R + 1 (one
+// dummy row on top).  Cost model (warp cycles per scored pair): a step costs ~15 FP32-pipe cycles
+// per row plus ~10 of per-step work; a haplotype takes H + G - 1 steps; a warp holds 32/G groups.
+// PHMM_FORCE_GROUP=16|32 restricts the choice (benchmarking aid).
+inline int pick_shape(int R, int H)
+{
+    static const int force = [] { const char* s = getenv("PHMM_FORCE_GROUP"); return s ? atoi(s) : 0; }();
+    int best = -1; double best_cost = 0;
+    for (int s = 0; s < kNumShapes; s++) {
+        const int G = kShapes[s].G, K = kShapes[s].K;
+        if (K * G < R + 1) continue;
+        if (force && G != force) continue;
+        const double cost = (double)G * (15.0 * K + 10.0) * (H + G - 1);
+        if (best < 0 || cost < best_cost) { best = s; best_cost = cost; }
+    }
+    if (best < 0 && force)      // forced width cannot hold this read: fall back to any feasible shape
+        for (int s = 0; s < kNumShapes; s++)
+            if (kShapes[s].K * kShapes[s].G >= R + 1) { best = s; break; }
+    return best;
+}
 
 // ---- grow-only buffers (the memory pool) ----------------------------------------------------
 struct PinnedBuf {
@@ -96,7 +113,7 @@ struct Part {
     uint8_t gap[3] = {0, 0, 0};              // the batch-constant (i, d, c) bytes when mode != general
     int max_H = 0, max_nh = 0;
     int n_jobs = 0;
-    int job_beg[kMaxRowsPerLane + 1] = {0};
+    int job_beg[kNumShapes + 1] = {0};      // jobs are grouped by shape
     int haps_per_job = 1, hap_chunks = 1;
     size_t h2d_bytes = 0, d2h_bytes = 0;
     int launches = 0;
@@ -277,34 +294,37 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
     p.mode = !constant ? kModeGeneral : (((p.gap[0] & 127) == (p.gap[1] & 127)) ? kModeConstShared : kModeConst);
     const bool general = p.mode == kModeGeneral;
 
-    // ---- plan: per region, reads of equal K are scored two at a time ----
-    std::vector<WarpJob> jobs_k[kMaxRowsPerLane];
+    // ---- plan: per region, reads that share a shape are scored 2 per lane group, 32/G groups per warp ----
+    std::vector<WarpJob> jobs_k[kNumShapes];
     for (int g = g0; g < g1; g++) {
-        int pending[kMaxRowsPerLane];
-        for (int k = 0; k < kMaxRowsPerLane; k++) pending[k] = -1;
+        WarpJob pending[kNumShapes];
+        int n_pending[kNumShapes];
+        for (int k = 0; k < kNumShapes; k++) n_pending[k] = 0;
         const int nh = b->region_hap_beg[g + 1] - b->region_hap_beg[g];
         p.max_nh = std::max(p.max_nh, nh);
         if (nh == 0) continue;
-        int64_t hap_sum = b->hap_off[b->region_hap_beg[g + 1]] - b->hap_off[b->region_hap_beg[g]];
+        const int64_t hap_sum = b->hap_off[b->region_hap_beg[g + 1]] - b->hap_off[b->region_hap_beg[g]];
+        const int h_avg = (int)(hap_sum / nh);
+        auto flush = [&](int k) {
+            WarpJob& j = pending[k];
+            j.region = g - g0;
+            for (int q = n_pending[k]; q < kMaxJobReads; q++) j.read[q] = -1;
+            jobs_k[k].push_back(j);
+            n_pending[k] = 0;
+        };
         for (int r = b->region_read_beg[g]; r < b->region_read_beg[g + 1]; r++) {
             const int R = b->read_off[r + 1] - b->read_off[r];
             p.n_cells += (int64_t)R * hap_sum;
-            const int k = rows_per_lane(R) - 1;
-            if (pending[k] < 0) { pending[k] = r - r0; continue; }
-            WarpJob j; j.region = g - g0; j.read[0] = pending[k]; j.read[1] = r - r0; j.read[2] = j.read[3] = -1;
-            jobs_k[k].push_back(j);
-            pending[k] = -1;
+            const int k = pick_shape(R, h_avg);
+            pending[k].read[n_pending[k]++] = r - r0;
+            if (n_pending[k] == 2 * (32 / kShapes[k].G)) flush(k);
         }
-        for (int k = 0; k < kMaxRowsPerLane; k++)
-            if (pending[k] >= 0) {
-                WarpJob j; j.region = g - g0; j.read[0] = pending[k]; j.read[1] = j.read[2] = j.read[3] = -1;
-                jobs_k[k].push_back(j);
-            }
+        for (int k = 0; k < kNumShapes; k++) if (n_pending[k]) flush(k);
     }
     for (int h = h0; h < h1; h++) p.max_H = std::max(p.max_H, b->hap_off[h + 1] - b->hap_off[h]);
     p.n_jobs = 0;
-    for (int k = 0; k < kMaxRowsPerLane; k++) { p.job_beg[k] = p.n_jobs; p.n_jobs += (int)jobs_k[k].size(); }
-    p.job_beg[kMaxRowsPerLane] = p.n_jobs;
+    for (int k = 0; k < kNumShapes; k++) { p.job_beg[k] = p.n_jobs; p.n_jobs += (int)jobs_k[k].size(); }
+    p.job_beg[kNumShapes] = p.n_jobs;
     {   // enough (job, hap-chunk) units to fill the chip several times over
         const int64_t target = (int64_t)dc.sm_count * 16 * 6;
         int chunks = (int)std::min<int64_t>(std::max<int64_t>(1, (target + p.n_jobs - 1) / std::max(1, p.n_jobs)), std::max(1, p.max_nh));
@@ -363,7 +383,7 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
         }
         std::memcpy(hp + o_haps, b->hap_bases + hb0, hap_bytes);
         WarpJob* jd = (WarpJob*)(hp + o_jobs);
-        for (int k = 0; k < kMaxRowsPerLane; k++)
+        for (int k = 0; k < kNumShapes; k++)
             if (!jobs_k[k].empty()) std::memcpy(jd + p.job_beg[k], jobs_k[k].data(), sizeof(WarpJob) * jobs_k[k].size());
     }
 
@@ -395,7 +415,7 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
     a.jobs = (const WarpJob*)(dp + o_jobs);
     a.n_jobs = 0;
     a.haps_per_job = p.haps_per_job;
-    a.smem_words_per_warp = (p.max_H + 31) / 32 * 32 + 2 * kGroupWidth + 32;   // slack: see staging in the kernel
+    a.smem_words_per_warp = (p.max_H + 31) / 32 * 32 + 2 * 32 + 32;   // slack: see staging in the kernel
     a.rescue_count = (unsigned*)s.d_out.p;
     a.raw32 = (float*)((uint8_t*)s.d_out.p + 16);
     a.rescue_out = (RescueOut*)s.d_rescue.p;
@@ -406,7 +426,7 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
 
     auto launch_all = [&](bool f64) -> int {
         const size_t smem = sizeof(uint32_t) * (size_t)a.smem_words_per_warp * kWarpsPerCta;
-        for (int k = 0; k < kMaxRowsPerLane; k++) {
+        for (int k = 0; k < kNumShapes; k++) {
             const int n = p.job_beg[k + 1] - p.job_beg[k];
             if (n == 0) continue;
             KernelFn fn = kernel_table().fn[f64 ? 1 : 0][exact ? 1 : 0][p.mode][k];
@@ -807,7 +827,7 @@ int phmm_run_staged(phmm_engine* e, phmm_staged* st, int32_t iters, float* ms_pe
                 launches = 0;
                 CUDA_TRY(cudaMemsetAsync(s.d_out.p, 0, 16, s.stream));
                 for (int f64 = 0; f64 < 2; f64++)
-                    for (int k = 0; k < kMaxRowsPerLane; k++) {
+                    for (int k = 0; k < kNumShapes; k++) {
                         const int n = p.job_beg[k + 1] - p.job_beg[k];
                         if (n == 0) continue;
                         KernelFn fn = kernel_table().fn[f64][exact ? 1 : 0][p.mode][k];

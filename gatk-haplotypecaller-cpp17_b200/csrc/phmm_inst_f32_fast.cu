@@ -1,5 +1,5 @@
-// phmm_inst_f32_fast.cu -- instantiates forward_kernel<PolicyF32x2, K=1..8, G=32, uniform/general, EXACT=false>.
+// phmm_inst_f32_fast.cu -- instantiates forward_kernel<PolicyF32x2, every Shape of phmm_launch.h, every MODE, EXACT=false>.
 #include "phmm_launch.h"
 namespace phmm {
-void register_f32_fast(KernelFn (*tab)[kMaxRowsPerLane]) { PHMM_REGISTER_ALL(PolicyF32x2, false); }
+void register_f32_fast(KernelTab& tab) { PHMM_REGISTER_ALL(PolicyF32x2, false); }
 }

@@ -38,6 +38,7 @@
 // is bit-identical to the reference's raw results.  FP32 is flush-to-zero (intel_pairhmm.hpp:102-105).
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 
 namespace phmm {
@@ -187,7 +188,10 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
 enum : int { kModeGeneral = 0, kModeConst = 1, kModeConstShared = 2 };
 
 template <class P, int K, int G, int MODE, bool EXACT>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+#ifndef PHMM_MIN_CTAS
+#define PHMM_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(kWarpsPerCta * 32, (P::kIsF32 && K <= 5) ? PHMM_MIN_CTAS : 1)
 forward_kernel(const KernelArgs args)
 {
     using S = typename P::S;
@@ -352,16 +356,14 @@ forward_kernel(const KernelArgs args)
             V dgM = inM, dgX = inX, dgY = inY;
             V sumM = P::splat(0), sumX = P::splat(0);
 
-            const int steps = H + G - 1;
-            // shared address of the word of column (t - l) is hp + 4 t
-            const uint32_t hp = (uint32_t)__cvta_generic_to_shared(hs) + 4u * (uint32_t)(G - l - 1);
-            uint32_t hw_next = lds_u32(hp + 4u);
-#pragma unroll 2
-            for (int t = 1; t <= steps; ++t) {
-                const int c = t - l;                        // this lane's column, 1-based
-                const uint32_t hw = hw_next;
-                hw_next = lds_u32(hp + 4u * (uint32_t)(t + 1));   // prefetch the next column's word
-                if ((unsigned)(c - 1) < (unsigned)H) {
+            // One step = this lane's next haplotype column (K cells), then hand the bottom row down.
+            // GUARD=true wraps the cell updates in the "is my column inside the haplotype" test
+            // (fill and drain of the wavefront); GUARD=false is the steady state where all G lanes
+            // are inside, compiled without any divergence so ptxas can overlap the X chain of one
+            // column with the independent work of the next.
+            auto step = [&](const uint32_t hw, const bool active, auto guard) {
+                constexpr bool GUARD = decltype(guard)::value;
+                if (!GUARD || active) {
                     // Phase A: everything that reads the previous column's state (so every old value
                     // is dead before it is overwritten: no register copies at the loop back-edge).
                     V t0[K];
@@ -414,6 +416,33 @@ forward_kernel(const KernelArgs args)
                 inM = P::shfl_up(M[K - 1], G);
                 inX = P::shfl_up(X[K - 1], G);
                 inY = P::shfl_up(Y[K - 1], G);
+            };
+
+            const int steps = H + G - 1;
+            // shared address of the word of column (t - l) is hp + 4 t
+            const uint32_t hp = (uint32_t)__cvta_generic_to_shared(hs) + 4u * (uint32_t)(G - l - 1);
+            int t = 1;
+            uint32_t hw_next = lds_u32(hp + 4u);            // every loop prefetches the next column's word
+            // fill: lanes enter one by one
+#pragma unroll 2
+            for (; t < G && t <= steps; ++t) {
+                const uint32_t hw = hw_next;
+                hw_next = lds_u32(hp + 4u * (uint32_t)(t + 1));
+                step(hw, (unsigned)(t - l - 1) < (unsigned)H, std::true_type{});
+            }
+            // steady state: every lane is inside the haplotype (columns G-l .. H-l, all within 1..H)
+#pragma unroll 4
+            for (; t <= H; ++t) {
+                const uint32_t hw = hw_next;
+                hw_next = lds_u32(hp + 4u * (uint32_t)(t + 1));
+                step(hw, true, std::false_type{});
+            }
+            // drain: lanes leave one by one
+#pragma unroll 2
+            for (; t <= steps; ++t) {
+                const uint32_t hw = hw_next;
+                hw_next = lds_u32(hp + 4u * (uint32_t)(t + 1));
+                step(hw, (unsigned)(t - l - 1) < (unsigned)H, std::true_type{});
             }
 
             if (l == G - 1) {
