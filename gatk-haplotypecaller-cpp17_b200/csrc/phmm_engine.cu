@@ -24,6 +24,7 @@
 #include <cmath>
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <functional>
@@ -39,6 +40,8 @@ using namespace phmm;
 namespace {
 
 constexpr size_t kAlign = 256;
+constexpr int kSmemBytesPerWarpBudget = 12 * 1024;   // 16 resident warps per SM within 227 KB
+constexpr int kPerHapTableBytes = 8 + 4 + 4 + 4;     // init_y, haplotype index, stream position, length
 inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 
 struct KernelTable {
@@ -125,7 +128,7 @@ struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
     PinnedBuf h_in, h_out, h_rescue;
-    DeviceBuf d_in, d_out, d_rescue;
+    DeviceBuf d_in, d_out, d_rescue, d_flags;
     bool busy = false;
     Part part;
     KernelArgs args{};
@@ -325,11 +328,17 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
     p.n_jobs = 0;
     for (int k = 0; k < kNumShapes; k++) { p.job_beg[k] = p.n_jobs; p.n_jobs += (int)jobs_k[k].size(); }
     p.job_beg[kNumShapes] = p.n_jobs;
-    {   // enough (job, hap-chunk) units to fill the chip several times over
-        const int64_t target = (int64_t)dc.sm_count * 16 * 6;
-        int chunks = (int)std::min<int64_t>(std::max<int64_t>(1, (target + p.n_jobs - 1) / std::max(1, p.n_jobs)), std::max(1, p.max_nh));
-        p.haps_per_job = (std::max(1, p.max_nh) + chunks - 1) / chunks;
-        p.hap_chunks = (std::max(1, p.max_nh) + p.haps_per_job - 1) / p.haps_per_job;
+    {   // Haplotypes streamed per (job, chunk): as many as possible (the wavefront fills and drains
+        // once per chunk), but enough (job, chunk) units to fill the chip ~8 times over, and a
+        // stream that fits the per-warp shared-memory budget.
+        const int64_t target = (int64_t)dc.sm_count * 16 * 8;
+        const int nhm = std::max(1, p.max_nh);
+        int chunks = (int)std::min<int64_t>(std::max<int64_t>(1, (target + p.n_jobs - 1) / std::max(1, p.n_jobs)), nhm);
+        int hpj = (nhm + chunks - 1) / chunks;
+        const int by_smem = std::max(1, (kSmemBytesPerWarpBudget - 2 * (kSkew * 31 + 2) - 16) / (p.max_H + 1 + kPerHapTableBytes));
+        hpj = std::min(hpj, by_smem);
+        p.haps_per_job = hpj;
+        p.hap_chunks = (nhm + hpj - 1) / hpj;
     }
 
     // ---- layout of the upload block ----
@@ -355,6 +364,7 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
     CUDA_TRY(s.h_out.reserve(out_bytes));
     CUDA_TRY(s.d_out.reserve(out_bytes));
     CUDA_TRY(s.d_rescue.reserve(sizeof(RescueOut) * (size_t)p.n_pairs));
+    CUDA_TRY(s.d_flags.reserve((size_t)p.n_jobs * p.hap_chunks + 16));
 
     uint8_t* hp = (uint8_t*)s.h_in.p;
     {
@@ -415,17 +425,20 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
     a.jobs = (const WarpJob*)(dp + o_jobs);
     a.n_jobs = 0;
     a.haps_per_job = p.haps_per_job;
-    a.smem_words_per_warp = (p.max_H + 31) / 32 * 32 + 2 * 32 + 32;   // slack: see staging in the kernel
+    a.stream_cap = (int32_t)((2 * (kSkew * 31 + 2) + (size_t)p.haps_per_job * (p.max_H + 1) + 15) / 16 * 16);
+    a.smem_bytes_per_warp = (int32_t)((a.stream_cap + (size_t)p.haps_per_job * kPerHapTableBytes + 15) / 16 * 16);
     a.rescue_count = (unsigned*)s.d_out.p;
     a.raw32 = (float*)((uint8_t*)s.d_out.p + 16);
     a.rescue_out = (RescueOut*)s.d_rescue.p;
+    a.job_flags = (uint8_t*)s.d_flags.p;
+    a.job_flag_base = 0;
 
     CUDA_TRY(cudaMemcpyAsync(s.d_in.p, s.h_in.p, in_bytes, cudaMemcpyHostToDevice, s.stream));
     p.h2d_bytes = in_bytes;
     if (!do_launch) return PHMM_OK;
 
     auto launch_all = [&](bool f64) -> int {
-        const size_t smem = sizeof(uint32_t) * (size_t)a.smem_words_per_warp * kWarpsPerCta;
+        const size_t smem = (size_t)a.smem_bytes_per_warp * kWarpsPerCta;
         for (int k = 0; k < kNumShapes; k++) {
             const int n = p.job_beg[k + 1] - p.job_beg[k];
             if (n == 0) continue;
@@ -433,6 +446,7 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
             KernelArgs ak = a;
             ak.jobs = a.jobs + p.job_beg[k];
             ak.n_jobs = n;
+            ak.job_flag_base = p.job_beg[k];
             if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             dim3 grid((n + kWarpsPerCta - 1) / kWarpsPerCta, p.hap_chunks);
             fn<<<grid, kWarpsPerCta * 32, smem, s.stream>>>(ak);
@@ -442,6 +456,7 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
         return PHMM_OK;
     };
     CUDA_TRY(cudaMemsetAsync(s.d_out.p, 0, 16, s.stream));
+    CUDA_TRY(cudaMemsetAsync(s.d_flags.p, 0, (size_t)p.n_jobs * p.hap_chunks, s.stream));
     CUDA_TRY(cudaEventRecord(s.ev_k0, s.stream));
     int rc = launch_all(false); if (rc) return rc;
     rc = launch_all(true); if (rc) return rc;
@@ -546,7 +561,7 @@ int init_device(DeviceCtx& dc, int depth, std::string& err)
 void free_slot(Slot& s)
 {
     s.h_in.release(); s.h_out.release(); s.h_rescue.release();
-    s.d_in.release(); s.d_out.release(); s.d_rescue.release();
+    s.d_in.release(); s.d_out.release(); s.d_rescue.release(); s.d_flags.release();
     if (s.ev_k0) cudaEventDestroy(s.ev_k0);
     if (s.ev_k1) cudaEventDestroy(s.ev_k1);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
@@ -821,12 +836,14 @@ int phmm_run_staged(phmm_engine* e, phmm_staged* st, int32_t iters, float* ms_pe
         Part& p = s.part;
         const bool exact = e->opt.exact_fp32 != 0;
         auto go = [&]() -> int {
-            const size_t smem = sizeof(uint32_t) * (size_t)s.args.smem_words_per_warp * kWarpsPerCta;
+            const size_t smem = (size_t)s.args.smem_bytes_per_warp * kWarpsPerCta;
             CUDA_TRY(cudaEventRecord(s.ev_k0, s.stream));
             for (int it = 0; it < iters; it++) {
                 launches = 0;
                 CUDA_TRY(cudaMemsetAsync(s.d_out.p, 0, 16, s.stream));
-                for (int f64 = 0; f64 < 2; f64++)
+                CUDA_TRY(cudaMemsetAsync(s.d_flags.p, 0, (size_t)p.n_jobs * p.hap_chunks, s.stream));
+                static const bool skip_rescue = getenv("PHMM_EXP_SKIP_RESCUE") != nullptr;   // timing experiments only
+                for (int f64 = 0; f64 < (skip_rescue ? 1 : 2); f64++)
                     for (int k = 0; k < kNumShapes; k++) {
                         const int n = p.job_beg[k + 1] - p.job_beg[k];
                         if (n == 0) continue;
@@ -834,6 +851,7 @@ int phmm_run_staged(phmm_engine* e, phmm_staged* st, int32_t iters, float* ms_pe
                         KernelArgs ak = s.args;
                         ak.jobs = s.args.jobs + p.job_beg[k];
                         ak.n_jobs = n;
+                        ak.job_flag_base = p.job_beg[k];
                         if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                         dim3 grid((n + kWarpsPerCta - 1) / kWarpsPerCta, p.hap_chunks);
                         fn<<<grid, kWarpsPerCta * 32, smem, s.stream>>>(ak);

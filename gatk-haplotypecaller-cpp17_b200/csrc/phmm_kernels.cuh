@@ -46,6 +46,10 @@ namespace phmm {
 constexpr int kWarpsPerCta = 4;
 constexpr int kMaxJobReads = 8;          // reads per warp job: 2 per lane group, up to 4 groups (G = 8)
 constexpr float kMinAccepted = 1e-28f;   // pairhmm/native/pairhmm_common.h:16
+// Lane l+1 runs kSkew columns behind lane l.  With 2, the bottom row a lane shuffles down at the end
+// of a step is not consumed until a whole step later, so the shuffle latency never sits on the
+// X-chain critical path (measured: the shuffles cost 17% at K=10 with a skew of 1).
+constexpr int kSkew = 2;
 
 struct WarpJob {
     int32_t region;
@@ -81,12 +85,16 @@ struct KernelArgs {
     // work list
     const WarpJob* jobs;
     int32_t n_jobs;
-    int32_t haps_per_job;
-    int32_t smem_words_per_warp;
+    int32_t haps_per_job;                // haplotypes streamed per (job, chunk)
+    int32_t stream_cap;                  // bytes of haplotype stream per warp (multiple of 16)
+    int32_t smem_bytes_per_warp;         // stream_cap + per-haplotype tables
     // results
     float*     raw32;                    // [n_pairs]
     RescueOut* rescue_out;               // [n_pairs] capacity
     unsigned*  rescue_count;
+    uint8_t*   job_flags;                // [n_jobs_total * hap_chunks]: 1 = some pair of this (job, chunk)
+                                         // underflowed in FP32, so the FP64 kernel has work there
+    int32_t    job_flag_base;            // index of this launch's first job in job_flags
 };
 
 // ---- precision policies --------------------------------------------------------------------
@@ -121,8 +129,12 @@ struct PolicyF32x2 {
         return make_float2(p0 ? a.x : b.x, p1 ? a.y : b.y);
     }
     __device__ static __forceinline__ V shfl_up(V v, int width) {
+#ifdef PHMM_EXP_NOSHFL   // timing experiment only (wrong results): how much do the shuffles cost?
+        return v;
+#else
         return make_float2(__shfl_up_sync(0xffffffffu, v.x, 1, width),
                            __shfl_up_sync(0xffffffffu, v.y, 1, width));
+#endif
     }
     __device__ static __forceinline__ S one() { return 1.0f; }
     __device__ static __forceinline__ S three() { return 3.0f; }
@@ -178,6 +190,19 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
     return v;
 }
 
+// a & b that the compiler cannot fold back into the 3-input LOP3 of every per-row test
+__device__ __forceinline__ uint32_t and_opaque(uint32_t a, uint32_t b) {
+    uint32_t v;
+    asm("and.b32 %0, %1, %2;" : "=r"(v) : "r"(a), "r"(b));
+    return v;
+}
+
+__device__ __forceinline__ uint32_t lds_u8(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
 // ---- the forward kernel ----------------------------------------------------------------------
 //
 // grid.x : warp jobs (kWarpsPerCta per CTA);  grid.y : haplotype chunks of args.haps_per_job
@@ -189,9 +214,9 @@ enum : int { kModeGeneral = 0, kModeConst = 1, kModeConstShared = 2 };
 
 template <class P, int K, int G, int MODE, bool EXACT>
 #ifndef PHMM_MIN_CTAS
-#define PHMM_MIN_CTAS 1
+#define PHMM_MIN_CTAS 4
 #endif
-__global__ void __launch_bounds__(kWarpsPerCta * 32, (P::kIsF32 && K <= 5) ? PHMM_MIN_CTAS : 1)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, (P::kIsF32 && K <= 5 && MODE != kModeGeneral) ? PHMM_MIN_CTAS : 1)
 forward_kernel(const KernelArgs args)
 {
     using S = typename P::S;
@@ -213,6 +238,8 @@ forward_kernel(const KernelArgs args)
     const int job_idx = blockIdx.x * kWarpsPerCta + warp;
     if (job_idx >= args.n_jobs) return;
 
+    uint8_t* const my_flag = args.job_flags + ((size_t)(args.job_flag_base + job_idx) * gridDim.y + blockIdx.y);
+    if (!P::kIsF32 && *my_flag == 0) return;               // nothing to redo here: one byte read, done
     const WarpJob job = args.jobs[job_idx];
     const int hap_beg = args.region_hap_beg[job.region];
     const int nh      = args.region_hap_beg[job.region + 1] - hap_beg;
@@ -221,7 +248,6 @@ forward_kernel(const KernelArgs args)
     const int h_last  = min(nh, h_first + args.haps_per_job);
     const int rd_beg  = args.region_read_beg[job.region];
     const int64_t out_base = args.region_out_beg[job.region];
-    uint32_t* hs = smem + warp * args.smem_words_per_warp;
 
     const S* __restrict__ ph2pr = P::ph2pr(args);
     const S* __restrict__ mmtab = P::mm(args);
@@ -312,35 +338,54 @@ forward_kernel(const KernelArgs args)
         const V pMX0 = (l == 0) ? P::splat(0) : pMX[0];
         const V pXX0 = (l == 0) ? P::splat(0) : (CONSTG ? pXXc : pYY[0]);
 
-        // ---- haplotypes of this chunk ----
+        // ---- haplotypes of this chunk, streamed back to back through ONE wavefront ----
+        // Shared memory (per warp): a byte stream
+        //     [LEAD x IDLE] hap_0 columns [NEXT] hap_1 columns [NEXT] ... hap_{n-1} columns [NEXT] [LEAD+1 x IDLE]
+        // with one one-hot nibble per column (A=1,C=2,T=4,G=8,N=15).  Lane l reads position
+        // t + kSkew (G-1-l) at step t, so lanes drop into the next haplotype one after the other while
+        // the lanes behind them are still finishing the previous one: the fill/drain bubbles of a
+        // wavefront are paid once per chunk, not once per pair.  A NEXT byte makes the lane hand over
+        // its result (last lane only) and reset to the column-0 state of the next haplotype; the
+        // bottom row it then shuffles down is exactly the (0, 0, y0) boundary the lane below needs.
+        uint8_t* sb   = reinterpret_cast<uint8_t*>(smem) + (size_t)warp * args.smem_bytes_per_warp;
+        S*   s_inity  = reinterpret_cast<S*>(sb + args.stream_cap);
+        int* s_hidx   = reinterpret_cast<int*>(s_inity + args.haps_per_job);
+        int* s_apos   = s_hidx + args.haps_per_job;
+        int* s_alen   = s_apos + args.haps_per_job;
+        constexpr uint8_t kSepNext = 0x10, kSepIdle = 0x20;
+
+        constexpr int LEAD = kSkew * (G - 1) + 1;          // idle bytes before / after the haplotypes
+        __syncwarp();
+        int n = 0, pos = LEAD;
 #pragma unroll 1
         for (int h = h_first; h < h_last; ++h) {
-            int64_t out_idx[NH];
-            bool want[NH];
-#pragma unroll
-            for (int hf = 0; hf < NH; ++hf) {
-                out_idx[hf] = out_base + (int64_t)(rd[hf] - rd_beg) * nh + h;
-                want[hf] = valid[hf] && group_live;
-            }
             if (!P::kIsF32) {
-                want[0] = want[0] && (args.raw32[out_idx[0]] < kMinAccepted);
-                if (!__any_sync(0xffffffffu, want[0])) continue;
+                const bool w = group_live && (args.raw32[out_base + (int64_t)(rd[0] - rd_beg) * nh + h] < kMinAccepted);
+                if (!__any_sync(0xffffffffu, w)) continue;     // nobody in this warp redoes this haplotype
             }
             const int ho = args.hap_off[hap_beg + h];
             const int H  = args.hap_off[hap_beg + h + 1] - ho;
+            for (int j = lane; j < H; j += 32) sb[pos + j] = (uint8_t)base_nibble(args.hap_bases[ho + j]);
+            if (lane == 0) {
+                sb[pos + H] = kSepNext;
+                s_inity[n] = P::sdiv(P::init_const(), (S)H);   // avx-pairhmm-template.h:86
+                s_hidx[n] = h; s_apos[n] = pos; s_alen[n] = H;
+            }
+            pos += H + 1; ++n;
+        }
+        if (n == 0) continue;
+        for (int j = lane; j < LEAD; j += 32) sb[j] = kSepIdle;
+        for (int j = lane; j <= LEAD; j += 32) sb[pos + j] = kSepIdle;
+        __syncwarp();
+        asm volatile("" ::: "memory");
+        const int p_end = pos - 1;                          // the NEXT byte closing the last haplotype
 
-            // stage: one replicated-nibble word per haplotype column, G words of slack in front
-            // (lanes still filling read below column 1) and G+1 behind (drain + prefetch)
-            __syncwarp();
-            for (int j = lane; j < H; j += 32)
-                hs[G + j] = base_nibble(args.hap_bases[ho + j]) * 0x11111111u;
-            __syncwarp();
-            asm volatile("" ::: "memory");
-
-            // column-0 state (avx-pairhmm-template.h:161-175): M = X = 0; Y = init_Y on row 0
-            const S init_y = P::sdiv(P::init_const(), (S)H);
-            V M[K], X[K], Y[K];
-            V Pm[SHARED ? K : 1];          // MODE 2: M * pMX (== M * pMY) of the previous column
+        // column-0 state (avx-pairhmm-template.h:161-175): M = X = 0; Y = init_Y on row 0 (dummy rows)
+        V M[K], X[K], Y[K];
+        V Pm[SHARED ? K : 1];             // MODE 2: M * pMX (== M * pMY) of the previous column
+        V sumM = P::splat(0), sumX = P::splat(0);
+        int jcur = 0;                     // haplotype (stream slot) this lane is in
+        auto reset_state = [&](const S init_y) {
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 M[k] = P::splat(0); X[k] = P::splat(0);
@@ -349,115 +394,144 @@ forward_kernel(const KernelArgs args)
                 for (int hf = 0; hf < NH; ++hf)
                     P::set(Y[k], hf, (l * K + k < pad[hf]) ? init_y : (S)0);
             }
-            // values of the row above this lane's first row: at the current column (in*) and at
-            // the previous column (dg*).  Lane 0 never uses them (its row 0 is a dummy row with
-            // zero priors, pMX0 = pXX0 = 0 and pYY = 1).
-            V inM = P::splat(0), inX = P::splat(0), inY = P::shfl_up(Y[K - 1], G);
-            V dgM = inM, dgX = inX, dgY = inY;
-            V sumM = P::splat(0), sumX = P::splat(0);
+            sumM = P::splat(0); sumX = P::splat(0);
+        };
+        reset_state(s_inity[0]);
+        // values of the row above this lane's first row: at the current column (in*) and at the
+        // previous column (dg*).  Lane 0 never uses them (its row 0 is a dummy row with zero
+        // priors, pMX0 = pXX0 = 0 and pYY = 1).
+        V inM = P::splat(0), inX = P::splat(0), inY = P::shfl_up(Y[K - 1], G);
+        V dgM = inM, dgX = inX, dgY = inY;
+        V qM = inM, qX = inX, qY = inY;   // kSkew == 2: bottom row in flight (sent last step, used next step)
 
-            // One step = this lane's next haplotype column (K cells), then hand the bottom row down.
-            // GUARD=true wraps the cell updates in the "is my column inside the haplotype" test
-            // (fill and drain of the wavefront); GUARD=false is the steady state where all G lanes
-            // are inside, compiled without any divergence so ptxas can overlap the X chain of one
-            // column with the independent work of the next.
-            auto step = [&](const uint32_t hw, const bool active, auto guard) {
-                constexpr bool GUARD = decltype(guard)::value;
-                if (!GUARD || active) {
-                    // Phase A: everything that reads the previous column's state (so every old value
-                    // is dead before it is overwritten: no register copies at the loop back-edge).
-                    V t0[K];
+        // K cell updates of this lane's current column
+        auto cells = [&](const uint32_t hw) {
+            // match bits of all K rows at once: (read nibbles & haplotype nibble); the per-row test
+            // below then reads ONE register (register-file read ports are the scarce resource)
+            uint32_t mh[NH][NW];
 #pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        const int kk = CONSTG ? 0 : k;
-                        const V dM = k ? M[k - 1] : dgM;    // (row-1, c-1)
-                        const V dX = k ? X[k - 1] : dgX;
-                        const V dY = k ? Y[k - 1] : dgY;
-                        if (EXACT) {
-                            // reference operation order, unfused (avx-pairhmm-template.h:188)
-                            t0[k] = P::addx(P::addx(P::mul(dM, pMM[kk]), P::mul(dX, pGAPM[kk])), P::mul(dY, pGAPM[kk]));
-                        } else {
-                            t0[k] = P::fma(dY, pGAPM[kk], P::fma(dX, pGAPM[kk], P::mul(dM, pMM[kk])));
-                        }
-                    }
-                    // Y from the left neighbour (:197); needs M of the previous column
+            for (int hf = 0; hf < NH; ++hf)
 #pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        const int kk = CONSTG ? 0 : k;
-                        const V yv = SHARED ? Pm[k] : P::mul(M[k], pMY[kk]);
-                        Y[k] = EXACT ? P::addx(yv, P::mul(Y[k], pYY[k])) : P::fma(Y[k], pYY[k], yv);
-                    }
-                    // Phase B: M = t0 * prior (prior select :152-158, scale :188)
+                for (int w = 0; w < NW; ++w) mh[hf][w] = and_opaque(rnib[hf][w], hw);
+            // Phase A: everything that reads the previous column's state (so every old value is dead
+            // before it is overwritten: no register copies at the loop back-edge).
+            V t0[K];
 #pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        const uint32_t field = 0xFu << (4 * (k % 8));
-                        const bool m0 = (rnib[0][k / 8] & hw & field) != 0;
-                        const bool m1 = (NH > 1) ? ((rnib[NH - 1][k / 8] & hw & field) != 0) : false;
-                        const V prior = P::sel(m0, m1, pr_mat[k], pr_mis[k]);
-                        M[k] = P::mul(t0[k], prior);
-                        if (SHARED) Pm[k] = P::mul(M[k], pMX[0]);
-                    }
-                    // Phase C: X runs down the column (cell above, :194)
-#pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        const int kk = CONSTG ? 0 : k;
-                        const V cXX = (k == 0) ? pXX0 : (CONSTG ? pXXc : pYY[k]);
-                        const V uX = k ? X[k - 1] : inX;    // (row-1, c)
-                        V um;                               // M(row-1, c) * pMX(row)
-                        if (k == 0) um = P::mul(inM, pMX0);
-                        else um = SHARED ? Pm[k - 1] : P::mul(M[k - 1], pMX[kk]);
-                        X[k] = EXACT ? P::addx(um, P::mul(uX, cXX)) : P::fma(uX, cXX, um);
-                    }
-                    // last row of the last lane is the last read row: running sums (:328-343)
-                    sumM = EXACT ? P::addx(sumM, M[K - 1]) : P::add(sumM, M[K - 1]);
-                    sumX = EXACT ? P::addx(sumX, X[K - 1]) : P::add(sumX, X[K - 1]);
+            for (int k = 0; k < K; ++k) {
+                const int kk = CONSTG ? 0 : k;
+                const V dM = k ? M[k - 1] : dgM;            // (row-1, c-1)
+                const V dX = k ? X[k - 1] : dgX;
+                const V dY = k ? Y[k - 1] : dgY;
+                if (EXACT) {
+                    // reference operation order, unfused (avx-pairhmm-template.h:188)
+                    t0[k] = P::addx(P::addx(P::mul(dM, pMM[kk]), P::mul(dX, pGAPM[kk])), P::mul(dY, pGAPM[kk]));
+                } else {
+                    t0[k] = P::fma(dY, pGAPM[kk], P::fma(dX, pGAPM[kk], P::mul(dM, pMM[kk])));
                 }
-                dgM = inM; dgX = inX; dgY = inY;
+            }
+            // Y from the left neighbour (:197); needs M of the previous column
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int kk = CONSTG ? 0 : k;
+                const V yv = SHARED ? Pm[k] : P::mul(M[k], pMY[kk]);
+#ifdef PHMM_EXP_YUNIFORM  // timing experiment only (wrong results): cost of the per-row pYY operand
+                Y[k] = P::fma(Y[k], pXXc, yv);
+#else
+                Y[k] = EXACT ? P::addx(yv, P::mul(Y[k], pYY[k])) : P::fma(Y[k], pYY[k], yv);
+#endif
+            }
+            // Phase B: M = t0 * prior (prior select :152-158, scale :188)
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const uint32_t field = 0xFu << (4 * (k % 8));
+                const bool m0 = (mh[0][k / 8] & field) != 0;
+                const bool m1 = (NH > 1) ? ((mh[NH - 1][k / 8] & field) != 0) : false;
+#ifdef PHMM_EXP_NOALU     // timing experiment only (wrong results): cost of the prior select
+                const V prior = pr_mat[k]; (void)m0; (void)m1;
+#else
+                const V prior = P::sel(m0, m1, pr_mat[k], pr_mis[k]);
+#endif
+                M[k] = P::mul(t0[k], prior);
+                if (SHARED) Pm[k] = P::mul(M[k], pMX[0]);
+            }
+            // Phase C: X runs down the column (cell above, :194)
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int kk = CONSTG ? 0 : k;
+                const V cXX = (k == 0) ? pXX0 : (CONSTG ? pXXc : pYY[k]);
+                const V uX = k ? X[k - 1] : inX;            // (row-1, c)
+                V um;                                       // M(row-1, c) * pMX(row)
+                if (k == 0) um = P::mul(inM, pMX0);
+                else um = SHARED ? Pm[k - 1] : P::mul(M[k - 1], pMX[kk]);
+                X[k] = EXACT ? P::addx(um, P::mul(uX, cXX)) : P::fma(uX, cXX, um);
+            }
+            // last row of the last lane is the last read row: running sums (:328-343)
+            sumM = EXACT ? P::addx(sumM, M[K - 1]) : P::add(sumM, M[K - 1]);
+            sumX = EXACT ? P::addx(sumX, X[K - 1]) : P::add(sumX, X[K - 1]);
+        };
+        // hand the bottom row to the lane below
+        auto rotate = [&]() {
+            dgM = inM; dgX = inX; dgY = inY;
+            if (kSkew == 2) {
+                inM = qM; inX = qX; inY = qY;
+                qM = P::shfl_up(M[K - 1], G);
+                qX = P::shfl_up(X[K - 1], G);
+                qY = P::shfl_up(Y[K - 1], G);
+            } else {
                 inM = P::shfl_up(M[K - 1], G);
                 inX = P::shfl_up(X[K - 1], G);
                 inY = P::shfl_up(Y[K - 1], G);
-            };
-
-            const int steps = H + G - 1;
-            // shared address of the word of column (t - l) is hp + 4 t
-            const uint32_t hp = (uint32_t)__cvta_generic_to_shared(hs) + 4u * (uint32_t)(G - l - 1);
-            int t = 1;
-            uint32_t hw_next = lds_u32(hp + 4u);            // every loop prefetches the next column's word
-            // fill: lanes enter one by one
-#pragma unroll 2
-            for (; t < G && t <= steps; ++t) {
-                const uint32_t hw = hw_next;
-                hw_next = lds_u32(hp + 4u * (uint32_t)(t + 1));
-                step(hw, (unsigned)(t - l - 1) < (unsigned)H, std::true_type{});
             }
-            // steady state: every lane is inside the haplotype (columns G-l .. H-l, all within 1..H)
-#pragma unroll 4
-            for (; t <= H; ++t) {
-                const uint32_t hw = hw_next;
-                hw_next = lds_u32(hp + 4u * (uint32_t)(t + 1));
-                step(hw, true, std::false_type{});
-            }
-            // drain: lanes leave one by one
-#pragma unroll 2
-            for (; t <= steps; ++t) {
-                const uint32_t hw = hw_next;
-                hw_next = lds_u32(hp + 4u * (uint32_t)(t + 1));
-                step(hw, (unsigned)(t - l - 1) < (unsigned)H, std::true_type{});
-            }
-
+        };
+        // a haplotype ends for this lane
+        auto boundary = [&]() {
             if (l == G - 1) {
+                const int h = s_hidx[jcur];
 #pragma unroll
                 for (int hf = 0; hf < NH; ++hf) {
-                    if (!want[hf]) continue;
+                    const int64_t oi = out_base + (int64_t)(rd[hf] - rd_beg) * nh + h;
+                    bool w = valid[hf] && group_live;
+                    if (!P::kIsF32) w = w && (args.raw32[oi] < kMinAccepted);
+                    if (!w) continue;
                     const S res = P::sadd(P::get(sumM, hf), P::get(sumX, hf));
                     if (P::kIsF32) {
-                        args.raw32[out_idx[hf]] = (float)res;
+                        args.raw32[oi] = (float)res;
+                        if ((float)res < kMinAccepted) *my_flag = 1;
                     } else {
                         const unsigned slot = atomicAdd(args.rescue_count, 1u);
-                        args.rescue_out[slot].out_idx = out_idx[hf];
+                        args.rescue_out[slot].out_idx = oi;
                         args.rescue_out[slot].raw64 = (double)res;
                     }
                 }
+            }
+            ++jcur;
+            reset_state(s_inity[min(jcur, n - 1)]);
+        };
+
+        // shared address of this lane's byte at step t is bp + t
+        const uint32_t bp = (uint32_t)__cvta_generic_to_shared(sb) + (uint32_t)(kSkew * (G - 1 - l));
+        int t = 0;
+        uint32_t b_next = lds_u8(bp);
+#pragma unroll 1
+        for (int j = 0; j <= n; ++j) {
+            // [t_a, t_s): every lane of the group is inside haplotype j -> no tests at all
+            const int t_a = (j < n) ? s_apos[j] : p_end + 1;
+            const int t_s = (j < n) ? t_a + s_alen[j] - kSkew * (G - 1) : t_a;
+            // lanes straddle two haplotypes (or the ends of the stream)
+#pragma unroll 1
+            for (; t < t_a; ++t) {
+                const uint32_t bcur = b_next;
+                b_next = lds_u8(bp + (uint32_t)(t + 1));
+                if (bcur & 0xFu) cells(bcur * 0x11111111u);
+                else if (bcur == kSepNext) boundary();
+                rotate();
+            }
+#pragma unroll 4
+            for (; t < t_s; ++t) {
+                const uint32_t bcur = b_next;
+                b_next = lds_u8(bp + (uint32_t)(t + 1));
+                cells(bcur * 0x11111111u);
+                rotate();
             }
         }
     }
