@@ -40,7 +40,7 @@ using namespace phmm;
 namespace {
 
 constexpr size_t kAlign = 256;
-constexpr int kSmemBytesPerWarpBudget = 12 * 1024;   // 16 resident warps per SM within 227 KB
+constexpr int kSmemBytesPerWarpBudget = 8 * 1024;    // haplotype stream share of the per-warp shared memory
 constexpr int kPerHapTableBytes = 8 + 4 + 4 + 4;     // init_y, haplotype index, stream position, length
 inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 
@@ -55,6 +55,12 @@ struct KernelTable {
     }
 };
 const KernelTable& kernel_table() { static KernelTable t; return t; }
+
+// per-warp dynamic shared memory of one shape: haplotype stream + prior tables + per-haplotype scalars
+inline int smem_bytes_per_warp(int stream_cap, int haps_per_job, Shape sh)
+{
+    return (stream_cap + tables_bytes(sh.K, sh.G) + haps_per_job * kPerHapTableBytes + 127) / 128 * 128;
+}
 
 // Shape for a read of R bases against haplotypes of about H bases.  Feasible: K*G >= R + 1 (one
 // dummy row on top).  Cost model (warp cycles per scored pair): a step costs ~15 FP32-pipe cycles
@@ -335,7 +341,7 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
         const int nhm = std::max(1, p.max_nh);
         int chunks = (int)std::min<int64_t>(std::max<int64_t>(1, (target + p.n_jobs - 1) / std::max(1, p.n_jobs)), nhm);
         int hpj = (nhm + chunks - 1) / chunks;
-        const int by_smem = std::max(1, (kSmemBytesPerWarpBudget - 2 * (kSkew * 31 + 2) - 16) / (p.max_H + 1 + kPerHapTableBytes));
+        const int by_smem = std::max(1, (kSmemBytesPerWarpBudget - 2 * (kSkew * 31 + 3) - 16) / (p.max_H + 1 + kPerHapTableBytes));
         hpj = std::min(hpj, by_smem);
         p.haps_per_job = hpj;
         p.hap_chunks = (nhm + hpj - 1) / hpj;
@@ -425,8 +431,8 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
     a.jobs = (const WarpJob*)(dp + o_jobs);
     a.n_jobs = 0;
     a.haps_per_job = p.haps_per_job;
-    a.stream_cap = (int32_t)((2 * (kSkew * 31 + 2) + (size_t)p.haps_per_job * (p.max_H + 1) + 15) / 16 * 16);
-    a.smem_bytes_per_warp = (int32_t)((a.stream_cap + (size_t)p.haps_per_job * kPerHapTableBytes + 15) / 16 * 16);
+    a.stream_cap = (int32_t)((2 * (kSkew * 31 + 3) + (size_t)p.haps_per_job * (p.max_H + 1) + 127) / 128 * 128);
+    a.smem_bytes_per_warp = 0;    // set per shape at launch (the prior tables depend on K and G)
     a.rescue_count = (unsigned*)s.d_out.p;
     a.raw32 = (float*)((uint8_t*)s.d_out.p + 16);
     a.rescue_out = (RescueOut*)s.d_rescue.p;
@@ -438,15 +444,17 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
     if (!do_launch) return PHMM_OK;
 
     auto launch_all = [&](bool f64) -> int {
-        const size_t smem = (size_t)a.smem_bytes_per_warp * kWarpsPerCta;
         for (int k = 0; k < kNumShapes; k++) {
             const int n = p.job_beg[k + 1] - p.job_beg[k];
             if (n == 0) continue;
+            const int per_warp = smem_bytes_per_warp(a.stream_cap, p.haps_per_job, kShapes[k]);
+            const size_t smem = (size_t)per_warp * kWarpsPerCta;
             KernelFn fn = kernel_table().fn[f64 ? 1 : 0][exact ? 1 : 0][p.mode][k];
             KernelArgs ak = a;
             ak.jobs = a.jobs + p.job_beg[k];
             ak.n_jobs = n;
             ak.job_flag_base = p.job_beg[k];
+            ak.smem_bytes_per_warp = per_warp;
             if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             dim3 grid((n + kWarpsPerCta - 1) / kWarpsPerCta, p.hap_chunks);
             fn<<<grid, kWarpsPerCta * 32, smem, s.stream>>>(ak);
@@ -836,7 +844,6 @@ int phmm_run_staged(phmm_engine* e, phmm_staged* st, int32_t iters, float* ms_pe
         Part& p = s.part;
         const bool exact = e->opt.exact_fp32 != 0;
         auto go = [&]() -> int {
-            const size_t smem = (size_t)s.args.smem_bytes_per_warp * kWarpsPerCta;
             CUDA_TRY(cudaEventRecord(s.ev_k0, s.stream));
             for (int it = 0; it < iters; it++) {
                 launches = 0;
@@ -848,7 +855,10 @@ int phmm_run_staged(phmm_engine* e, phmm_staged* st, int32_t iters, float* ms_pe
                         const int n = p.job_beg[k + 1] - p.job_beg[k];
                         if (n == 0) continue;
                         KernelFn fn = kernel_table().fn[f64][exact ? 1 : 0][p.mode][k];
+                        const int per_warp = smem_bytes_per_warp(s.args.stream_cap, p.haps_per_job, kShapes[k]);
+                        const size_t smem = (size_t)per_warp * kWarpsPerCta;
                         KernelArgs ak = s.args;
+                        ak.smem_bytes_per_warp = per_warp;
                         ak.jobs = s.args.jobs + p.job_beg[k];
                         ak.n_jobs = n;
                         ak.job_flag_base = p.job_beg[k];

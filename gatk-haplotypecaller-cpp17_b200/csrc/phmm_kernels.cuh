@@ -15,10 +15,14 @@
 //     issue slots for the 2 LOP3 + 2 FSEL per cell pair that pick the match/mismatch prior
 //     (measured on B200: FFMA and FFMA2 both saturate at ~125 lane-FMAs/clk/SM, integer/select ops
 //     at 64/clk/SM -- profiles/r01_microbench_pipes.txt);
-//   * the haplotype is staged once per warp in shared memory as one 32-bit word per column holding
-//     the base's one-hot nibble replicated 8 times (A=1,C=2,T=4,G=8,N=15), the K read bases of a
-//     lane are packed as nibbles of one register, so "bases equal or either is N"
-//     (avx-pairhmm-template.h:3-35,70-75) is a single LOP3 with predicate output per cell;
+//   * the match/mismatch prior (avx-pairhmm-template.h:3-35,70-75,152-158) is NOT selected with
+//     integer/select instructions: ncu showed every LOP3/FSEL paying 1-2 extra dispatch-stall cycles
+//     behind the FFMA2s (register-file read ports), ~30% of the kernel.  Instead each read pair gets
+//     a shared-memory table prior[hap base A,C,T,G,N][row] (both packed reads side by side), built
+//     once per job; a step fetches its K priors with LDS.128 from the sub-table its haplotype base
+//     names (the haplotype is staged as one byte per column holding that sub-table's offset).  The
+//     LSU path is otherwise idle, the loads are conflict-free (odd 16-byte lane stride, 128-byte
+//     aligned sub-tables) and the 2K prior registers of the select scheme are gone;
 //   * gap penalties: the reference only ever passes the constant strings 'I','I','+' (sam/sam.hpp:30-32),
 //     so MODE 1/2 take ONE (i,d,c) triple per batch and keep the five transition factors in
 //     warp-uniform operands.  That matters beyond register count: measured on B200, FFMA2 with three
@@ -172,36 +176,39 @@ struct PolicyF64 {
     __device__ static __forceinline__ S cg(const KernelArgs& a, int i) { return a.cg_d[i]; }
 };
 
-// base byte -> one-hot nibble; everything that is not A,C,T,G,N is 'A' (pairhmm_common.h:26-44)
-__device__ __forceinline__ uint32_t base_nibble(uint8_t b) {
-    uint32_t n = 1u;
-    n = (b == 'C') ? 2u : n;
-    n = (b == 'T') ? 4u : n;
-    n = (b == 'G') ? 8u : n;
-    n = (b == 'N') ? 15u : n;
-    return n;
-}
-
-// Shared-memory word load by 32-bit shared address.  Keeps the haplotype cursor in ONE register
-// (the generic-pointer form made ptxas rebuild the shared window base every step: S2UR+UMOV+ULEA+LEA).
-__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
-    return v;
-}
-
-// a & b that the compiler cannot fold back into the 3-input LOP3 of every per-row test
-__device__ __forceinline__ uint32_t and_opaque(uint32_t a, uint32_t b) {
-    uint32_t v;
-    asm("and.b32 %0, %1, %2;" : "=r"(v) : "r"(a), "r"(b));
-    return v;
-}
-
+// Shared-memory loads by 32-bit shared address (keeps each cursor in ONE register; the generic
+// pointer form made ptxas rebuild the shared window base every step).
 __device__ __forceinline__ uint32_t lds_u8(uint32_t saddr) {
     uint32_t v;
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
     return v;
 }
+template <class V>
+__device__ __forceinline__ void lds_2v(uint32_t saddr, V& a, V& b) {   // 16 bytes = two 8-byte V
+    unsigned long long x, y;
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "r"(saddr));
+    a = *reinterpret_cast<V*>(&x);
+    b = *reinterpret_cast<V*>(&y);
+}
+
+// base byte -> table index; everything that is not A,C,T,G,N is 'A' (pairhmm_common.h:26-44)
+__device__ __forceinline__ int base_code(uint8_t b) {
+    int n = 0;
+    n = (b == 'C') ? 1 : n;
+    n = (b == 'T') ? 2 : n;
+    n = (b == 'G') ? 3 : n;
+    n = (b == 'N') ? 4 : n;
+    return n;
+}
+
+// ---- shared-memory geometry of one shape (host and device agree through these) ----------------
+// Prior table of one lane group: 5 sub-tables (haplotype base A,C,T,G,N), each holding for every
+// lane its K priors (V = 8 bytes: both packed reads) at a lane stride of an ODD number of 16-byte
+// units, so the 8 lanes of an LDS.128 quarter-warp hit 8 distinct bank groups.
+__host__ __device__ constexpr int lane_units(int K) { return (((K + 1) / 2) % 2) ? (K + 1) / 2 : (K + 1) / 2 + 1; }
+__host__ __device__ constexpr int subtable_bytes(int K, int G) { return (G * lane_units(K) * 16 + 127) / 128 * 128; }
+__host__ __device__ constexpr int tables_bytes(int K, int G) { return (32 / G) * 5 * subtable_bytes(K, G); }
+constexpr int kStreamNext = 0x80, kStreamIdle = 0x81;   // stream bytes >= 0x80 are not columns
 
 // ---- the forward kernel ----------------------------------------------------------------------
 //
@@ -209,13 +216,13 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t saddr) {
 // One warp = 32/G lane groups.  FP32: group g scores reads job.read[2g], job.read[2g+1] together.
 // FP64 (rescue): group g redoes job.read[2g] and then job.read[2g+1], each only for the haplotypes
 // whose raw FP32 result is below 1e-28f (intel_pairhmm.hpp:137); it reads that decision straight
-// from args.raw32, so no work list is built between the two kernels.
+// from args.raw32 (and a per-(job,chunk) flag byte), so no work list is built between the kernels.
 enum : int { kModeGeneral = 0, kModeConst = 1, kModeConstShared = 2 };
 
-template <class P, int K, int G, int MODE, bool EXACT>
 #ifndef PHMM_MIN_CTAS
 #define PHMM_MIN_CTAS 4
 #endif
+template <class P, int K, int G, int MODE, bool EXACT>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, (P::kIsF32 && K <= 5 && MODE != kModeGeneral) ? PHMM_MIN_CTAS : 1)
 forward_kernel(const KernelArgs args)
 {
@@ -225,12 +232,15 @@ forward_kernel(const KernelArgs args)
     constexpr int NG = 32 / G;
     constexpr bool CONSTG = MODE != kModeGeneral;
     constexpr bool SHARED = MODE == kModeConstShared;
-    constexpr int NW = (K + 7) / 8;       // registers holding the K read-base nibbles
     constexpr int KP = CONSTG ? 1 : K;    // per-row factor arrays collapse to one warp-uniform entry
+    constexpr int SUBT = subtable_bytes(K, G);
+    constexpr int LANE_B = lane_units(K) * 16;
     static_assert(K >= 1 && K <= 16, "K rows per lane");
     static_assert(NG * 2 <= kMaxJobReads, "job too small for this group width");
+    static_assert(4 * (SUBT / 128) < 128, "sub-table offset must fit the stream byte");
+    static_assert(sizeof(V) == 8, "prior table entries are 8 bytes");
 
-    extern __shared__ uint32_t smem[];
+    extern __shared__ __align__(16) uint8_t smem[];
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int grp  = lane / G;
@@ -251,6 +261,15 @@ forward_kernel(const KernelArgs args)
 
     const S* __restrict__ ph2pr = P::ph2pr(args);
     const S* __restrict__ mmtab = P::mm(args);
+
+    // per-warp shared memory: [haplotype stream | prior tables | per-haplotype scalars]
+    uint8_t* sb   = smem + (size_t)warp * args.smem_bytes_per_warp;
+    uint8_t* stab = sb + args.stream_cap;
+    S*   s_inity  = reinterpret_cast<S*>(stab + tables_bytes(K, G));
+    int* s_hidx   = reinterpret_cast<int*>(s_inity + args.haps_per_job);
+    int* s_apos   = s_hidx + args.haps_per_job;
+    int* s_alen   = s_apos + args.haps_per_job;
+    V* const my_tab = reinterpret_cast<V*>(stab + grp * 5 * SUBT + l * LANE_B);   // + b * SUBT, [k]
 
     constexpr int NSUB = 2 / NH;         // FP64: the two reads of a group one after the other
 #pragma unroll 1
@@ -275,61 +294,63 @@ forward_kernel(const KernelArgs args)
 #pragma unroll
         for (int hf = 1; hf < NH; ++hf) if (!valid[hf]) rd[hf] = rd[0];
 
-        // ---- per-row registers: priors and transition factors (avx-pairhmm-template.h:83-128) ----
-        V pr_mat[K], pr_mis[K];           // 1 - dist, dist / 3   (0 on dummy rows)
+        // ---- per-row setup (avx-pairhmm-template.h:83-128): transition factors in registers,
+        //      priors (1 - dist on a match, dist / 3 otherwise; 0 on dummy rows) into the table ----
         V pYY[K];                         // Y self-transition (1 on dummy rows).  In MODE 0 it is
                                           // also the row's X self-transition (pXX == pYY, :117,:119)
         V pMM[KP], pGAPM[KP], pMX[KP], pMY[KP];
         V pXXc = P::splat(0);             // MODE 1/2: X self-transition of every row
-        uint32_t rnib[NH][NW];            // K read-base nibbles per packed read
         int pad[NH];
         if (CONSTG) {
             pMM[0] = P::splat(P::cg(args, 0)); pGAPM[0] = P::splat(P::cg(args, 1));
             pMX[0] = P::splat(P::cg(args, 2)); pMY[0] = P::splat(P::cg(args, 3));
             pXXc   = P::splat(P::cg(args, 4));
         }
+        __syncwarp();                     // previous sub / previous user of this warp's tables is done
+        {
 #pragma unroll
-        for (int hf = 0; hf < NH; ++hf) {
-            const int r  = rd[hf];
-            const int ro = args.read_off[r];
-            const int R  = args.read_off[r + 1] - ro;
-            pad[hf] = K * G - R;          // >= 1 by construction of the plan
+            for (int hf = 0; hf < NH; ++hf) {
+                const int r  = rd[hf];
+                const int ro = args.read_off[r];
+                const int R  = args.read_off[r + 1] - ro;
+                pad[hf] = K * G - R;      // >= 1 by construction of the plan
 #pragma unroll
-            for (int w = 0; w < NW; ++w) rnib[hf][w] = 0;
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const int ri = l * K + k - pad[hf];
-                S mat = 0, mis = 0, yy = P::one();
-                S mm_ = 0, gapm = 0, mx_ = 0, my_ = 0;
-                uint32_t nib = 0;
-                if (ri >= 0) {
-                    nib = base_nibble(args.read_bases[ro + ri]);
-                    const S dist = ph2pr[args.read_q[ro + ri] & 127];
-                    mat = P::ssub(P::one(), dist);
-                    mis = P::sdiv(dist, P::three());
-                    if (!CONSTG) {
-                        const int gi = args.read_i[ro + ri] & 127;
-                        const int gd = args.read_d[ro + ri] & 127;
-                        const int gc = args.read_c[ro + ri] & 127;
-                        const int mx = max(gi, gd), mn = min(gi, gd);
-                        mm_  = mmtab[((mx * (mx + 1)) >> 1) + mn];
-                        gapm = P::ssub(P::one(), ph2pr[gc]);
-                        mx_  = ph2pr[gi];
-                        my_  = ph2pr[gd];
-                        yy   = ph2pr[gc];
-                    } else {
-                        yy = P::cg(args, 4);
+                for (int k = 0; k < K; ++k) {
+                    const int ri = l * K + k - pad[hf];
+                    S mat = 0, mis = 0, yy = P::one();
+                    S mm_ = 0, gapm = 0, mx_ = 0, my_ = 0;
+                    int rc = 4;
+                    if (ri >= 0) {
+                        rc = base_code(args.read_bases[ro + ri]);
+                        const S dist = ph2pr[args.read_q[ro + ri] & 127];
+                        mat = P::ssub(P::one(), dist);
+                        mis = P::sdiv(dist, P::three());
+                        if (!CONSTG) {
+                            const int gi = args.read_i[ro + ri] & 127;
+                            const int gd = args.read_d[ro + ri] & 127;
+                            const int gc = args.read_c[ro + ri] & 127;
+                            const int mx = max(gi, gd), mn = min(gi, gd);
+                            mm_  = mmtab[((mx * (mx + 1)) >> 1) + mn];
+                            gapm = P::ssub(P::one(), ph2pr[gc]);
+                            mx_  = ph2pr[gi];
+                            my_  = ph2pr[gd];
+                            yy   = ph2pr[gc];
+                        } else {
+                            yy = P::cg(args, 4);
+                        }
                     }
-                }
-                rnib[hf][k / 8] |= nib << (4 * (k % 8));
-                P::set(pr_mat[k], hf, mat);
-                P::set(pr_mis[k], hf, mis);
-                P::set(pYY[k], hf, yy);
-                if (!CONSTG) {
-                    P::set(pMM[k], hf, mm_);
-                    P::set(pGAPM[k], hf, gapm);
-                    P::set(pMX[k], hf, mx_);
-                    P::set(pMY[k], hf, my_);
+                    // prior table entry [haplotype base b][row]: half hf of an 8-byte V
+#pragma unroll
+                    for (int b = 0; b < 5; ++b)   // N on either side matches (:11,:21-26)
+                        reinterpret_cast<S*>(reinterpret_cast<uint8_t*>(my_tab) + b * SUBT + k * 8)[hf] =
+                            (rc == 4 || b == 4 || rc == b) ? mat : mis;
+                    P::set(pYY[k], hf, yy);
+                    if (!CONSTG) {
+                        P::set(pMM[k], hf, mm_);
+                        P::set(pGAPM[k], hf, gapm);
+                        P::set(pMX[k], hf, mx_);
+                        P::set(pMY[k], hf, my_);
+                    }
                 }
             }
         }
@@ -340,22 +361,15 @@ forward_kernel(const KernelArgs args)
 
         // ---- haplotypes of this chunk, streamed back to back through ONE wavefront ----
         // Shared memory (per warp): a byte stream
-        //     [LEAD x IDLE] hap_0 columns [NEXT] hap_1 columns [NEXT] ... hap_{n-1} columns [NEXT] [LEAD+1 x IDLE]
-        // with one one-hot nibble per column (A=1,C=2,T=4,G=8,N=15).  Lane l reads position
-        // t + kSkew (G-1-l) at step t, so lanes drop into the next haplotype one after the other while
-        // the lanes behind them are still finishing the previous one: the fill/drain bubbles of a
-        // wavefront are paid once per chunk, not once per pair.  A NEXT byte makes the lane hand over
-        // its result (last lane only) and reset to the column-0 state of the next haplotype; the
-        // bottom row it then shuffles down is exactly the (0, 0, y0) boundary the lane below needs.
-        uint8_t* sb   = reinterpret_cast<uint8_t*>(smem) + (size_t)warp * args.smem_bytes_per_warp;
-        S*   s_inity  = reinterpret_cast<S*>(sb + args.stream_cap);
-        int* s_hidx   = reinterpret_cast<int*>(s_inity + args.haps_per_job);
-        int* s_apos   = s_hidx + args.haps_per_job;
-        int* s_alen   = s_apos + args.haps_per_job;
-        constexpr uint8_t kSepNext = 0x10, kSepIdle = 0x20;
-
+        //     [LEAD x IDLE] hap_0 columns [NEXT] hap_1 columns [NEXT] ... hap_{n-1} columns [NEXT] [LEAD+2 x IDLE]
+        // one byte per column = 128-byte offset of the prior sub-table of that column's base.
+        // Lane l reads position t + kSkew (G-1-l) at step t, so lanes drop into the next haplotype
+        // one after the other while the lanes behind them are still finishing the previous one: the
+        // fill/drain bubbles of a wavefront are paid once per chunk, not once per pair.  A NEXT byte
+        // makes the lane hand over its result (last lane only) and reset to the column-0 state of
+        // the next haplotype; the bottom row it then shuffles down is exactly the (0, 0, y0)
+        // boundary the lane below needs.
         constexpr int LEAD = kSkew * (G - 1) + 1;          // idle bytes before / after the haplotypes
-        __syncwarp();
         int n = 0, pos = LEAD;
 #pragma unroll 1
         for (int h = h_first; h < h_last; ++h) {
@@ -365,17 +379,18 @@ forward_kernel(const KernelArgs args)
             }
             const int ho = args.hap_off[hap_beg + h];
             const int H  = args.hap_off[hap_beg + h + 1] - ho;
-            for (int j = lane; j < H; j += 32) sb[pos + j] = (uint8_t)base_nibble(args.hap_bases[ho + j]);
+            for (int j = lane; j < H; j += 32)
+                sb[pos + j] = (uint8_t)(base_code(args.hap_bases[ho + j]) * (SUBT / 128));
             if (lane == 0) {
-                sb[pos + H] = kSepNext;
+                sb[pos + H] = (uint8_t)kStreamNext;
                 s_inity[n] = P::sdiv(P::init_const(), (S)H);   // avx-pairhmm-template.h:86
                 s_hidx[n] = h; s_apos[n] = pos; s_alen[n] = H;
             }
             pos += H + 1; ++n;
         }
         if (n == 0) continue;
-        for (int j = lane; j < LEAD; j += 32) sb[j] = kSepIdle;
-        for (int j = lane; j <= LEAD; j += 32) sb[pos + j] = kSepIdle;
+        for (int j = lane; j < LEAD; j += 32) sb[j] = (uint8_t)kStreamIdle;
+        for (int j = lane; j <= LEAD + 1; j += 32) sb[pos + j] = (uint8_t)kStreamIdle;
         __syncwarp();
         asm volatile("" ::: "memory");
         const int p_end = pos - 1;                          // the NEXT byte closing the last haplotype
@@ -404,15 +419,15 @@ forward_kernel(const KernelArgs args)
         V dgM = inM, dgX = inX, dgY = inY;
         V qM = inM, qX = inX, qY = inY;   // kSkew == 2: bottom row in flight (sent last step, used next step)
 
-        // K cell updates of this lane's current column
-        auto cells = [&](const uint32_t hw) {
-            // match bits of all K rows at once: (read nibbles & haplotype nibble); the per-row test
-            // below then reads ONE register (register-file read ports are the scarce resource)
-            uint32_t mh[NH][NW];
+        const uint32_t tab_addr = (uint32_t)__cvta_generic_to_shared(my_tab);
+        // K cell updates of this lane's current column; `cb` is the column's stream byte
+        auto cells = [&](const uint32_t cb) {
+            // priors of this column: K entries of the sub-table the haplotype base names.  Issued
+            // first; phase A below (4K FP32-pipe instructions) covers the LDS latency.
+            V prior[K + 1];
+            const uint32_t pa = tab_addr + (cb << 7);
 #pragma unroll
-            for (int hf = 0; hf < NH; ++hf)
-#pragma unroll
-                for (int w = 0; w < NW; ++w) mh[hf][w] = and_opaque(rnib[hf][w], hw);
+            for (int k = 0; k < K; k += 2) lds_2v<V>(pa + 8u * k, prior[k], prior[k + 1]);
             // Phase A: everything that reads the previous column's state (so every old value is dead
             // before it is overwritten: no register copies at the loop back-edge).
             V t0[K];
@@ -434,24 +449,12 @@ forward_kernel(const KernelArgs args)
             for (int k = 0; k < K; ++k) {
                 const int kk = CONSTG ? 0 : k;
                 const V yv = SHARED ? Pm[k] : P::mul(M[k], pMY[kk]);
-#ifdef PHMM_EXP_YUNIFORM  // timing experiment only (wrong results): cost of the per-row pYY operand
-                Y[k] = P::fma(Y[k], pXXc, yv);
-#else
                 Y[k] = EXACT ? P::addx(yv, P::mul(Y[k], pYY[k])) : P::fma(Y[k], pYY[k], yv);
-#endif
             }
-            // Phase B: M = t0 * prior (prior select :152-158, scale :188)
+            // Phase B: M = t0 * prior (:152-158, :188)
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                const uint32_t field = 0xFu << (4 * (k % 8));
-                const bool m0 = (mh[0][k / 8] & field) != 0;
-                const bool m1 = (NH > 1) ? ((mh[NH - 1][k / 8] & field) != 0) : false;
-#ifdef PHMM_EXP_NOALU     // timing experiment only (wrong results): cost of the prior select
-                const V prior = pr_mat[k]; (void)m0; (void)m1;
-#else
-                const V prior = P::sel(m0, m1, pr_mat[k], pr_mis[k]);
-#endif
-                M[k] = P::mul(t0[k], prior);
+                M[k] = P::mul(t0[k], prior[k]);
                 if (SHARED) Pm[k] = P::mul(M[k], pMX[0]);
             }
             // Phase C: X runs down the column (cell above, :194)
@@ -522,15 +525,15 @@ forward_kernel(const KernelArgs args)
             for (; t < t_a; ++t) {
                 const uint32_t bcur = b_next;
                 b_next = lds_u8(bp + (uint32_t)(t + 1));
-                if (bcur & 0xFu) cells(bcur * 0x11111111u);
-                else if (bcur == kSepNext) boundary();
+                if (bcur < 0x80u) cells(bcur);
+                else if (bcur == (uint32_t)kStreamNext) boundary();
                 rotate();
             }
 #pragma unroll 4
             for (; t < t_s; ++t) {
                 const uint32_t bcur = b_next;
                 b_next = lds_u8(bp + (uint32_t)(t + 1));
-                cells(bcur * 0x11111111u);
+                cells(bcur);
                 rotate();
             }
         }
