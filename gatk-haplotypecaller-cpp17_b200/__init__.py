@@ -165,6 +165,26 @@ class Batch:
         per_base = 5 if self.explicit_gaps else 2
         return int(per_base * len(self.read_bases) + len(self.hap_bases))
 
+    def region_cells(self):
+        """Cell count (sum of read_len x hap_len over pairs) of every region."""
+        rl = np.concatenate([[0], np.cumsum(np.diff(self.read_off).astype(np.int64))])
+        hl = np.concatenate([[0], np.cumsum(np.diff(self.hap_off).astype(np.int64))])
+        return (rl[self.region_read_beg[1:]] - rl[self.region_read_beg[:-1]]) * \
+               (hl[self.region_hap_beg[1:]] - hl[self.region_hap_beg[:-1]])
+
+    def slice_regions(self, g0, g1):
+        """Regions [g0, g1) as their own Batch (offsets rebased); outputs keep their relative order."""
+        r0, r1 = int(self.region_read_beg[g0]), int(self.region_read_beg[g1])
+        h0, h1 = int(self.region_hap_beg[g0]), int(self.region_hap_beg[g1])
+        b0, b1 = int(self.read_off[r0]), int(self.read_off[r1])
+        c0, c1 = int(self.hap_off[h0]), int(self.hap_off[h1])
+        kw = dict(gap_open_i=self.gap_open_i, gap_open_d=self.gap_open_d, gap_cont_c=self.gap_cont_c)
+        if self.explicit_gaps:
+            kw.update(read_i=self.read_i[b0:b1], read_d=self.read_d[b0:b1], read_c=self.read_c[b0:b1])
+        return Batch(self.region_read_beg[g0:g1 + 1] - r0, self.region_hap_beg[g0:g1 + 1] - h0,
+                     self.read_off[r0:r1 + 1] - b0, self.read_bases[b0:b1], self.read_q[b0:b1],
+                     self.hap_off[h0:h1 + 1] - c0, self.hap_bases[c0:c1], **kw)
+
     def c_struct(self):
         p = lambda a: a.ctypes.data_as(C.c_void_p)
         b = _Batch()
@@ -310,9 +330,34 @@ class PairHMMEngine:
         return lik[idx], idx
 
 
+def shard_bounds(cells, world):
+    """Contiguous split of regions over `world` ranks balanced by cell count (no exchange between
+    ranks: every pair is independent, intel_pairhmm.hpp:131-147).  Same rule as the engine's own
+    multi-device split (phmm_engine.cu: split_regions).  Returns world+1 region boundaries."""
+    pre = np.concatenate([[0], np.cumsum(np.asarray(cells, np.int64))])
+    total, n = int(pre[-1]), len(cells)
+    cut, g = [0], 0
+    for d in range(1, world):
+        want = total * d // world
+        while g < n and pre[g + 1] <= want:
+            g += 1
+        if g < n and (want - pre[g]) > (pre[g + 1] - want):
+            g += 1
+        cut.append(max(cut[-1], g))
+    cut.append(n)
+    return cut
+
+
+def shard_regions(batch, rank, world):
+    """The sub-batch rank `rank` of `world` computes, and the offset of its outputs in the whole batch."""
+    cut = shard_bounds(batch.region_cells(), world)
+    g0, g1 = cut[rank], cut[rank + 1]
+    return batch.slice_regions(g0, g1), int(batch.region_out_beg[g0])
+
+
 def normalize_filter(lik, read_len):
     """In-place cap at best-4.5 and poorly-modelled-read flags (intel_pairhmm.hpp:24-46), host side."""
-    lik = np.ascontiguousarray(lik, np.float64)
+    assert lik.dtype == np.float64 and lik.flags["C_CONTIGUOUS"], "in-place: needs a contiguous float64 matrix"
     n_reads, n_haps = lik.shape
     keep = np.zeros(n_reads, np.uint8)
     rl = np.ascontiguousarray(read_len, np.int32)

@@ -1,0 +1,95 @@
+"""CPU suite, part 2: host logic and the C-ABI library surface (no compute calls: no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    hdr = open(os.path.join(ROOT, "include", "phmm.h")).read()
+    declared = set(re.findall(r"^\s*(?:const\s+char\*|int|void)\s+(phmm_\w+)\s*\(", hdr, re.M))
+    assert declared >= {"phmm_create", "phmm_destroy", "phmm_compute", "phmm_submit", "phmm_wait", "phmm_strerror"}
+    L = pkg.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), f"libphmm_b200.so does not export {name}"
+    assert declared == set(pkg.EXPORTS)
+    assert L.phmm_abi_version() == 1
+
+
+def test_only_sm100a_code_in_the_library(pkg):
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", pkg.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_strerror_and_no_cpu_fallback(pkg):
+    L = pkg.lib()
+    assert L.phmm_strerror(0) == b"ok"
+    assert b"no CPU fallback" in L.phmm_strerror(2)
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(pkg.PhmmError) as ei:       # creating an engine must fail loudly, never fall back
+        pkg.PairHMMEngine()
+    assert ei.value.code == 2
+
+
+def test_batch_container(pkg):
+    b = pkg.Batch.from_regions([([b"ACGT", b"AC"], [b"FFFF", b"FF"], [b"ACGTA", b"AC", b"A"]),
+                                ([b"TTT"], [b"III"], [b"TTTT"])])
+    assert (b.n_regions, b.n_reads, b.n_haps, b.n_pairs) == (2, 3, 4, 7)
+    assert b.n_cells == (4 + 2) * (5 + 2 + 1) + 3 * 4
+    assert b.region_out_beg.tolist() == [0, 6, 7]
+    assert not b.explicit_gaps and b.read_i.tolist() == [ord("I")] * 9 and b.read_c.tolist() == [ord("+")] * 9
+    s = b.slice_regions(1, 2)
+    assert (s.n_regions, s.n_reads, s.n_haps) == (1, 1, 1) and bytes(s.read_bases) == b"TTT" and bytes(s.hap_bases) == b"TTTT"
+    cs = b.c_struct()
+    assert cs.n_reads == 3 and not cs.read_i and cs.gap_open_i == ord("I") and cs.gap_cont_c == ord("+")
+
+
+def test_synthetic_generators_match_the_named_shapes(pkg):
+    s2, s3 = pkg.synth.s2(3), pkg.synth.s3(2)
+    assert s2.reads_per_region.tolist() == [64] * 3 and s2.haps_per_region.tolist() == [8] * 3
+    assert set(np.diff(s2.read_off)) == {100} and set(np.diff(s2.hap_off)) == {300}
+    assert s3.reads_per_region.tolist() == [256] * 2 and s3.haps_per_region.tolist() == [16] * 2
+    assert set(np.diff(s3.read_off)) == {150} and set(np.diff(s3.hap_off)) == {500}
+    assert s3.n_cells == 2 * 256 * 16 * 150 * 500
+    assert pkg.synth.s3(2).read_bases.tobytes() == s3.read_bases.tobytes()          # seeded
+    q = s3.read_q.astype(int) - 33
+    assert q.min() >= 20 and q.max() <= 40
+    s4 = pkg.synth.s4(2, n_reads=5, n_haps=3)
+    rl, hl = np.diff(s4.read_off), np.diff(s4.hap_off)
+    assert rl.min() >= 150 and rl.max() <= 250 and hl.min() >= 600 and hl.max() <= 1000
+    g = pkg.synth.s3(1, general_gaps=True)
+    assert g.explicit_gaps and len(set(g.read_i.tolist())) > 1
+    tot = sum(b.n_regions for b in pkg.synth.s5_stream(20, windows_per_batch=8))
+    assert tot == 20
+
+
+def test_shard_bounds_balance_and_cover(pkg):
+    b = pkg.synth.random_small(5, n_regions=23)
+    cells = b.region_cells()
+    assert int(cells.sum()) == b.n_cells
+    for world in (1, 2, 3, 4, 8):
+        cut = pkg.shard_bounds(cells, world)
+        assert cut[0] == 0 and cut[-1] == b.n_regions and all(x <= y for x, y in zip(cut, cut[1:]))
+        offs = [pkg.shard_regions(b, r, world)[1] for r in range(world)]
+        sizes = [pkg.shard_regions(b, r, world)[0].n_pairs for r in range(world)]
+        assert offs == np.concatenate([[0], np.cumsum(sizes)])[:-1].tolist() and sum(sizes) == b.n_pairs
+    big = pkg.synth.s2(64)
+    per = [pkg.shard_regions(big, r, 8)[0].n_cells for r in range(8)]
+    assert max(per) == min(per)                     # equal regions -> exact balance
+
+
+def test_normalize_filter_semantics(pkg):
+    # intel_pairhmm.hpp:24-46: cap at best-4.5; drop when best < min(2, ceil(0.02 len)) * -4
+    lik = np.array([[-1.0, -9.0, -5.5], [-9.0, -20.0, -8.5], [-4.0, -4.0, -4.0]])
+    keep = pkg.normalize_filter(lik, np.array([100, 100, 10], np.int32))
+    assert lik[0].tolist() == [-1.0, -5.5, -5.5]
+    assert keep.tolist() == [1, 0, 1]               # thresholds: -8, -8, -4 (best == threshold is kept)
+    assert lik[1].tolist() == [-9.0, -13.0, -8.5]

@@ -1,0 +1,213 @@
+"""GPU suite (-m gpu): the CUDA path through the C ABI (phmm_compute / submit / wait / staged) against
+the oracle and the committed golden fixtures.
+
+Bars (BASELINE.json north_star): |log10 - oracle| <= 1e-4 on the FP32 path, <= 1e-9 on FP64-rescued
+pairs, identical rescue decisions; and with exact_fp32=1 the raw FP32 forward sums are BIT-IDENTICAL
+to the reference (and so is every rescue decision by construction).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL32, TOL64 = 1e-4, 1e-9
+
+
+def _maxerr(a, b):
+    if not len(a):
+        return 0.0
+    d = np.where(a == b, 0.0, np.abs(a - b))       # equal infinities count as zero
+    return float(np.nan_to_num(d, nan=np.inf).max())
+
+
+def check(got, want, exact=False, what=""):
+    resc = want["rescued"].astype(bool)
+    assert np.array_equal(got.rescued.astype(bool), resc), f"{what}: rescue decisions differ"
+    assert _maxerr(got.log10[~resc], want["log10"][~resc]) <= TOL32, what
+    assert _maxerr(got.log10[resc], want["log10"][resc]) <= TOL64, what
+    if exact:
+        assert np.array_equal(got.raw32.view(np.uint32), want["raw32"].view(np.uint32)), f"{what}: raw FP32 bits"
+        assert np.array_equal(got.log10[~resc].view(np.uint64), want["log10"][~resc].view(np.uint64)), what
+    assert got.stats["kernel_launches"] > 0 and got.stats["n_pairs"] == len(want["log10"])
+    assert got.stats["n_rescued"] == int(resc.sum())
+
+
+def _kat_batch(pkg, kats):
+    return pkg.Batch.from_regions([([k["read"].encode()], [k["qual"].encode()], [k["hap"].encode()]) for k in kats])
+
+
+def test_kat_appendix_a_through_the_c_abi(pkg, engine, exact_engine, golden):
+    kats = golden["kat_appendix_a"]["a1"]
+    b = _kat_batch(pkg, kats)
+    ex = exact_engine.compute(b)
+    assert ex.raw32.view(np.uint32).tolist() == [k["f32_bits"] for k in kats]
+    assert ex.rescued.tolist() == [k["rescue"] for k in kats]
+    fast = engine.compute(b)
+    assert fast.rescued.tolist() == [k["rescue"] for k in kats]
+    l32, l64 = golden["kat_appendix_a"]["log10_init_f32"], golden["kat_appendix_a"]["log10_init_f64"]
+    for k, v, e in zip(kats, fast.log10, ex.log10):
+        if k["rescue"]:
+            want = np.log10(np.array([k["f64_bits"]], np.uint64).view(np.float64)[0]) - l64
+            assert abs(v - want) <= TOL64 and abs(e - want) <= TOL64, k["name"]
+        else:
+            f = np.array([k["f32_bits"]], np.uint32).view(np.float32)[0]
+            want = float(np.float32(np.log10(f, dtype=np.float32)) - np.float32(l32))
+            assert abs(v - want) <= TOL32 and abs(e - want) <= TOL32, k["name"]
+
+
+def test_golden_reference_pairs(pkg, engine, exact_engine, golden):
+    for g in golden["ref_random_pairs"]["batches"]:
+        b = pkg.synth.random_small(g["seed"], **g["kw"])
+        want = {"raw32": np.array(g["raw32_bits"], np.uint32).view(np.float32),
+                "log10": np.array(g["log10_bits"], np.uint64).view(np.float64),
+                "rescued": np.array(g["rescued"], np.uint8)}
+        check(engine.compute(b), want, what=f"golden seed {g['seed']} fast")
+        check(exact_engine.compute(b), want, exact=True, what=f"golden seed {g['seed']} exact")
+
+
+@pytest.mark.parametrize("seed,kw", [
+    (1, dict(n_regions=6)),                                              # per-base gap penalties, N bases
+    (2, dict(n_regions=6, general_gaps=False)),                          # the reference's constant 'I','I','+'
+    (3, dict(n_regions=8, max_read_len=255, max_hap_len=600)),           # longest single-pass read, long haps
+    (4, dict(n_regions=5, lower_frac=0.1, n_frac=0.1)),                  # lower case -> 'A', many N
+    (5, dict(n_regions=12, max_reads=1, max_haps=1)),                    # 1 x 1 regions (odd counts everywhere)
+    (6, dict(n_regions=4, max_read_len=3, max_hap_len=3)),               # tiny R and H, reads longer than haps
+    (7, dict(n_regions=3, max_reads=40, max_haps=20, general_gaps=False)),
+])
+def test_random_ragged_batches(pkg, engine, exact_engine, oracle, seed, kw):
+    b = pkg.synth.random_small(seed, **kw)
+    want = oracle.batch(b, threads=8)
+    check(engine.compute(b), want, what=f"seed {seed} fast")
+    check(exact_engine.compute(b), want, exact=True, what=f"seed {seed} exact")
+
+
+def test_constant_but_unequal_gap_penalties(pkg, engine, exact_engine, oracle):
+    """Batch-constant (i,d,c) with i != d takes kernel MODE 1; NULL arrays and explicit constant arrays agree."""
+    b = pkg.synth.random_small(31, n_regions=4, general_gaps=False)
+    kw = dict(gap_open_i=ord("I"), gap_open_d=ord("F"), gap_cont_c=ord("-"))
+    b1 = pkg.Batch(b.region_read_beg, b.region_hap_beg, b.read_off, b.read_bases, b.read_q, b.hap_off, b.hap_bases, **kw)
+    n = len(b.read_bases)
+    b2 = pkg.Batch(b.region_read_beg, b.region_hap_beg, b.read_off, b.read_bases, b.read_q, b.hap_off, b.hap_bases,
+                   read_i=np.full(n, ord("I"), np.uint8), read_d=np.full(n, ord("F"), np.uint8), read_c=np.full(n, ord("-"), np.uint8))
+    want = oracle.batch(b1)
+    check(exact_engine.compute(b1), want, exact=True, what="mode 1 NULL arrays")
+    check(exact_engine.compute(b2), want, exact=True, what="mode 1 explicit arrays")
+    check(engine.compute(b2), want, what="mode 1 fast")
+
+
+@pytest.mark.parametrize("name,make", [
+    ("S2 100x300 64x8", lambda s: s.s2(4)),
+    ("S3 150x500 256x16", lambda s: s.s3(2)),
+    ("S3 general gaps", lambda s: s.s3(1, general_gaps=True)),
+    ("S4 long, all rescued", lambda s: s.s4(2, n_reads=24, n_haps=4)),
+    ("S4 general gaps", lambda s: s.s4(1, n_reads=12, n_haps=3, general_gaps=True)),
+    ("S5 window stream", lambda s: next(s.s5_stream(6, windows_per_batch=6))),
+])
+def test_baseline_shapes_vs_oracle(pkg, engine, exact_engine, oracle, name, make):
+    b = make(pkg.synth)
+    want = oracle.batch(b, threads=16)
+    check(engine.compute(b), want, what=name)
+    check(exact_engine.compute(b), want, exact=True, what=name + " exact")
+    if name.startswith("S4"):
+        assert want["rescued"].all()
+
+
+def test_full_size_s3_properties(pkg, engine, oracle):
+    """BASELINE config 3 at full size (64 regions, 1.97e10 cells): size-independent properties plus an
+    oracle spot check (the oracle would need minutes for the whole batch)."""
+    b = pkg.synth.s3(64)
+    got = engine.compute(b)
+    assert got.stats["n_cells"] == 64 * 256 * 16 * 150 * 500
+    # (1) batch-split invariance: every region computed alone gives the same bits
+    for g in (0, 31, 63):
+        alone = engine.compute(b.slice_regions(g, g + 1))
+        o = int(b.region_out_beg[g])
+        assert np.array_equal(alone.log10.view(np.uint64), got.log10[o:o + alone.log10.size].view(np.uint64))
+    # (2) read-order invariance inside a region: pairs are independent, whatever lane partner they get
+    reg = b.slice_regions(5, 6)
+    nr, nh, R = 256, 16, 150
+    perm = np.random.default_rng(0).permutation(nr)
+    shuf = pkg.Batch(reg.region_read_beg, reg.region_hap_beg, reg.read_off,
+                     reg.read_bases.reshape(nr, R)[perm].reshape(-1), reg.read_q.reshape(nr, R)[perm].reshape(-1),
+                     reg.hap_off, reg.hap_bases)
+    a = engine.compute(reg).log10.reshape(nr, nh)
+    s = engine.compute(shuf).log10.reshape(nr, nh)
+    assert np.array_equal(a[perm].view(np.uint64), s.view(np.uint64))
+    # (3) duplicated haplotype -> duplicated column
+    dup = pkg.Batch(reg.region_read_beg, [0, 2], reg.read_off, reg.read_bases, reg.read_q, [0, 500, 1000],
+                    np.concatenate([reg.hap_bases[:500], reg.hap_bases[:500]]))
+    d = engine.compute(dup).log10.reshape(nr, 2)
+    assert np.array_equal(d[:, 0].view(np.uint64), d[:, 1].view(np.uint64))
+    assert np.array_equal(d[:, 0].view(np.uint64), a[:, 0].view(np.uint64))
+    # (4) oracle spot check on 3 whole regions
+    for g in (7, 40):
+        sub = b.slice_regions(g, g + 1)
+        want = oracle.batch(sub, threads=16)
+        o = int(b.region_out_beg[g])
+        resc = want["rescued"].astype(bool)
+        assert np.array_equal(got.rescued[o:o + sub.n_pairs].astype(bool), resc)
+        assert _maxerr(got.log10[o:o + sub.n_pairs][~resc], want["log10"][~resc]) <= TOL32
+        assert _maxerr(got.log10[o:o + sub.n_pairs][resc], want["log10"][resc]) <= TOL64
+
+
+def test_call_surface_compute_likelihoods(pkg, engine, golden):
+    """hc::IntelPairHMM::compute_likelihoods semantics (cap at best-4.5, poorly modelled reads erased)
+    against the reference's own outputs (Appendix A.2 + six regions)."""
+    a2 = golden["kat_appendix_a"]["a2"]
+    regions = [dict(a2, lik_bits=np.array(a2["lik"]).reshape(-1).view(np.uint64).tolist())] + golden["ref_region_filter"]["regions"]
+    for reg in regions:
+        lik, kept = engine.compute_likelihoods([h.encode() for h in reg["haps"]], [r.encode() for r in reg["reads"]],
+                                               [q.encode() for q in reg["quals"]])
+        assert kept.tolist() == [i for i, k in enumerate(reg["keep"]) if k]
+        want = np.array(reg["lik_bits"], np.uint64).view(np.float64).reshape(lik.shape)
+        assert _maxerr(lik, want) <= TOL32
+
+
+def test_submit_wait_pipeline_and_staged_path(pkg, engine, oracle):
+    batches = [pkg.synth.random_small(50 + i, n_regions=5, general_gaps=bool(i % 2)) for i in range(6)]
+    sync = [engine.compute(b).log10 for b in batches]
+    # two tickets in flight (pipeline depth 2), waited in order
+    t0 = engine.submit(batches[0])
+    for i in range(1, len(batches)):
+        t1 = engine.submit(batches[i])
+        assert np.array_equal(engine.wait(t0).log10.view(np.uint64), sync[i - 1].view(np.uint64))
+        t0 = t1
+    assert np.array_equal(engine.wait(t0).log10.view(np.uint64), sync[-1].view(np.uint64))
+    # device-resident form gives the same bits as the host-buffer form
+    st = engine.stage(batches[2])
+    ms, launches = engine.run_staged(st, 2)
+    res = engine.fetch_staged(st, batches[2].n_pairs)
+    engine.free_staged(st)
+    assert ms > 0 and launches > 0
+    assert np.array_equal(res.log10.view(np.uint64), sync[2].view(np.uint64))
+
+
+def test_edge_cases_and_errors(pkg, engine, oracle):
+    B = pkg.Batch
+    # regions without reads or without haplotypes contribute no pairs; empty batch is fine
+    b = B.from_regions([([], [], [b"ACGT"]), ([b"ACGT"], [b"FFFF"], []), ([b"ACGT"], [b"FFFF"], [b"ACGT"])])
+    got = engine.compute(b)
+    assert got.log10.size == 1 and abs(got.log10[0] - oracle.batch(b)["log10"][0]) <= TOL32
+    assert engine.compute(B.from_regions([])).log10.size == 0
+    # one-base read, one-base haplotype
+    b = B.from_regions([([b"A", b"C"], [b"I", b"#"], [b"A", b"N", b"ACGTACGT"])])
+    check(engine.compute(b), oracle.batch(b), what="1-base")
+    # longest supported read (255) against a long haplotype
+    rng = np.random.default_rng(9)
+    hap = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 3000)]
+    rd = hap[100:355].copy()
+    b = B.from_regions([([rd], [np.full(255, 63, np.uint8)], [hap, hap[:700]])])
+    check(engine.compute(b), oracle.batch(b), what="R=255 H=3000")
+    # errors: read too long -> UNSUPPORTED (5); empty read -> INVALID_ARG (1); bad ticket (6)
+    with pytest.raises(pkg.PhmmError) as ei:
+        engine.compute(B.from_regions([([np.full(256, 65, np.uint8)], [np.full(256, 70, np.uint8)], [b"ACGT"])]))
+    assert ei.value.code == 5
+    with pytest.raises(pkg.PhmmError) as ei:
+        engine.compute(B.from_regions([([b""], [b""], [b"ACGT"])]))
+    assert ei.value.code == 1
+    with pytest.raises(pkg.PhmmError) as ei:
+        engine.wait(123456)
+    assert ei.value.code == 6
+    # the engine is still healthy afterwards
+    b = B.from_regions([([b"ACGT"], [b"FFFF"], [b"ACGT"])])
+    check(engine.compute(b), oracle.batch(b), what="after errors")
