@@ -1,0 +1,55 @@
+"""The C++17 host mirror (include/b200_pairhmm.hpp): hc::B200PairHMM::compute_likelihoods with the
+reference's call signature (pairhmm/intel_pairhmm.hpp:48-56), over the C ABI."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "gatk-haplotypecaller-cpp17_b200")
+
+
+@pytest.fixture(scope="module")
+def exe(tmp_path_factory, pkg):
+    out = str(tmp_path_factory.mktemp("cpp") / "host_mirror_main")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([cxx, "-std=c++17", "-O2", "-Wall", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "host_mirror_main.cpp"), "-o", out,
+                    "-L" + PKG, "-lphmm_b200", "-Wl,-rpath," + PKG], check=True)
+    return out
+
+
+def _region_file(path, reg):
+    with open(path, "w") as f:
+        for h in reg["haps"]:
+            f.write(f"H {h}\n")
+        for r, q in zip(reg["reads"], reg["quals"]):
+            f.write(f"R {r} {q}\n")
+
+
+def test_header_compiles_and_fails_loudly_without_gpu(exe, tmp_path, golden):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    p = tmp_path / "r.txt"
+    _region_file(p, golden["kat_appendix_a"]["a2"])
+    r = subprocess.run([exe, str(p)], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr       # never a silent CPU path
+
+
+@pytest.mark.gpu
+def test_cpp_mirror_matches_reference_call_surface(exe, tmp_path, golden):
+    a2 = golden["kat_appendix_a"]["a2"]
+    regions = [dict(a2, lik_bits=np.array(a2["lik"]).reshape(-1).view(np.uint64).tolist())] + golden["ref_region_filter"]["regions"]
+    for i, reg in enumerate(regions):
+        p = tmp_path / f"r{i}.txt"
+        _region_file(p, reg)
+        r = subprocess.run([exe, str(p)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        lines = r.stdout.strip().splitlines()
+        kept = [int(x) for x in lines[0].split()[1:]]
+        assert kept == [k for k, f in enumerate(reg["keep"]) if f]            # reads erased like :40-45
+        got = np.array([[float(x) for x in ln.split()] for ln in lines[1:]]).reshape(len(kept), -1)
+        want = np.array(reg["lik_bits"], np.uint64).view(np.float64).reshape(got.shape)
+        assert np.abs(got - want).max() <= 1e-4
