@@ -35,7 +35,7 @@ if len(rows) > 2:
     agg = collections.defaultdict(collections.Counter); tot = 0
     reasons = ["stall_math", "stall_wait", "stall_not_selected", "stall_selected", "stall_dispatch", "stall_short_sb", "stall_long_sb", "stall_branch_resolving", "stall_mio", "stall_no_inst"]
     for r in rows[2:]:
-        if len(r) < len(hdr): continue
+        if len(r) < len(hdr) or r[ix["# Samples"]] == "# Samples": continue   # later kernels repeat the header
         parts = r[ix["Source"]].split()
         if not parts: continue
         op = parts[1] if parts[0].startswith("@") else parts[0]
