@@ -47,7 +47,12 @@
 
 namespace phmm {
 
-constexpr int kWarpsPerCta = 4;
+#ifndef PHMM_WARPS_PER_CTA
+#define PHMM_WARPS_PER_CTA 1
+#endif
+// One warp per CTA: warps never cooperate, and single-warp CTAs let the block scheduler fill every SM
+// sub-partition evenly at any register count (measured +9% on S3 over 4-warp CTAs at 186 registers).
+constexpr int kWarpsPerCta = PHMM_WARPS_PER_CTA;
 constexpr int kMaxJobReads = 8;          // reads per warp job: 2 per lane group, up to 4 groups (G = 8)
 constexpr float kMinAccepted = 1e-28f;   // pairhmm/native/pairhmm_common.h:16
 // Lane l+1 runs kSkew columns behind lane l.  With 2, the bottom row a lane shuffles down at the end
@@ -219,11 +224,11 @@ constexpr int kStreamNext = 0x80, kStreamIdle = 0x81;   // stream bytes >= 0x80 
 // from args.raw32 (and a per-(job,chunk) flag byte), so no work list is built between the kernels.
 enum : int { kModeGeneral = 0, kModeConst = 1, kModeConstShared = 2 };
 
-#ifndef PHMM_MIN_CTAS
-#define PHMM_MIN_CTAS 4
+#ifndef PHMM_MIN_WARPS
+#define PHMM_MIN_WARPS 16      // resident warps per SM the small-K constant-gap FP32 kernels are held to
 #endif
 template <class P, int K, int G, int MODE, bool EXACT>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, (P::kIsF32 && K <= 5 && MODE != kModeGeneral) ? PHMM_MIN_CTAS : 1)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, (P::kIsF32 && K <= 5 && MODE != kModeGeneral) ? PHMM_MIN_WARPS / kWarpsPerCta : 1)
 forward_kernel(const KernelArgs args)
 {
     using S = typename P::S;
