@@ -45,7 +45,7 @@ constexpr int kPerHapTableBytes = 8 + 4 + 4 + 4;     // init_y, haplotype index,
 inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 
 struct KernelTable {
-    // [f64][exact] -> [mode][shape]
+    // [f64][exact] -> [mode][aligned][shape]
     KernelTab fn[2][2];
     KernelTable() {
         register_f32_fast(fn[0][0]);
@@ -122,7 +122,7 @@ struct Part {
     uint8_t gap[3] = {0, 0, 0};              // the batch-constant (i, d, c) bytes when mode != general
     int max_H = 0, max_nh = 0;
     int n_jobs = 0;
-    int job_beg[kNumShapes + 1] = {0};      // jobs are grouped by shape
+    int job_beg[2 * kNumShapes + 1] = {0};  // jobs are grouped by kernel slot = shape + kNumShapes * aligned
     int haps_per_job = 1, hap_chunks = 1;
     size_t h2d_bytes = 0, d2h_bytes = 0;
     int launches = 0;
@@ -130,8 +130,12 @@ struct Part {
     unsigned rescue_count = 0;
 };
 
+constexpr int kAuxStreams = 4;      // kernels of different shapes of one batch run side by side
+
 struct Slot {
     cudaStream_t stream = nullptr;
+    cudaStream_t aux[kAuxStreams] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[kAuxStreams] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
     PinnedBuf h_in, h_out, h_rescue;
     DeviceBuf d_in, d_out, d_rescue, d_flags;
@@ -271,6 +275,58 @@ int64_t region_cells(const phmm_batch* b, int g)
     return (int64_t)(b->read_off[r1] - b->read_off[r0]) * (b->hap_off[h1] - b->hap_off[h0]);
 }
 
+// Forward (FP32) and rescue (FP64) kernels of a staged slot.  Every kernel slot (shape x aligned) is an
+// independent launch pair; they are spread over a few auxiliary streams forked from / joined to the
+// slot's stream so that the small grids of a ragged batch overlap.  ev_k0 / ev_k1 bracket the lot.
+int launch_kernels(Slot& s, bool exact, bool skip_rescue, std::string& err)
+{
+    Part& p = s.part;
+    const KernelArgs& a = s.args;
+    p.launches = 0;
+    CUDA_TRY(cudaMemsetAsync(s.d_out.p, 0, 16, s.stream));
+    CUDA_TRY(cudaMemsetAsync(s.d_flags.p, 0, (size_t)p.n_jobs * p.hap_chunks, s.stream));
+    CUDA_TRY(cudaEventRecord(s.ev_k0, s.stream));
+    int n_kernels = 0;
+    for (int k = 0; k < 2 * kNumShapes; k++) n_kernels += (p.job_beg[k + 1] > p.job_beg[k]);
+    const bool fork = n_kernels > 1;
+    bool used[kAuxStreams] = {false, false, false, false};
+    if (fork) CUDA_TRY(cudaEventRecord(s.ev_fork, s.stream));
+    int which = 0;
+    for (int k = 0; k < 2 * kNumShapes; k++) {
+        const int n = p.job_beg[k + 1] - p.job_beg[k];
+        if (n == 0) continue;
+        cudaStream_t st = s.stream;
+        if (fork) {
+            const int ai = which++ % kAuxStreams;
+            st = s.aux[ai];
+            if (!used[ai]) { CUDA_TRY(cudaStreamWaitEvent(st, s.ev_fork, 0)); used[ai] = true; }
+        }
+        const int per_warp = smem_bytes_per_warp(a.stream_cap, p.haps_per_job, kShapes[k % kNumShapes]);
+        const size_t smem = (size_t)per_warp * kWarpsPerCta;
+        KernelArgs ak = a;
+        ak.jobs = a.jobs + p.job_beg[k];
+        ak.n_jobs = n;
+        ak.job_flag_base = p.job_beg[k];
+        ak.smem_bytes_per_warp = per_warp;
+        dim3 grid((n + kWarpsPerCta - 1) / kWarpsPerCta, p.hap_chunks);
+        for (int f64 = 0; f64 < (skip_rescue ? 1 : 2); f64++) {      // the FP64 redo follows its FP32 pass
+            KernelFn fn = kernel_table().fn[f64][exact ? 1 : 0][p.mode][k / kNumShapes][k % kNumShapes];
+            if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            fn<<<grid, kWarpsPerCta * 32, smem, st>>>(ak);
+            CUDA_TRY(cudaGetLastError());
+            p.launches++;
+        }
+    }
+    if (fork)
+        for (int ai = 0; ai < kAuxStreams; ai++)
+            if (used[ai]) {
+                CUDA_TRY(cudaEventRecord(s.ev_join[ai], s.aux[ai]));
+                CUDA_TRY(cudaStreamWaitEvent(s.stream, s.ev_join[ai], 0));
+            }
+    CUDA_TRY(cudaEventRecord(s.ev_k1, s.stream));
+    return PHMM_OK;
+}
+
 // Pack regions [g0,g1) of the batch into the slot's pinned block, upload, launch, start D2H.
 int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1, int64_t out0,
                      bool exact, bool do_launch, std::string& err)
@@ -304,11 +360,30 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
     const bool general = p.mode == kModeGeneral;
 
     // ---- plan: per region, reads that share a shape are scored 2 per lane group, 32/G groups per warp ----
-    std::vector<WarpJob> jobs_k[kNumShapes];
+    constexpr int kSlots = 2 * kNumShapes;
+    auto is_aligned = [&](int R, int sh) {
+        return !general && (R % kShapes[sh].K == 0) && (kShapes[sh].K * kShapes[sh].G - R >= kShapes[sh].K);
+    };
+    bool use_aligned[kNumShapes];
+    {
+        int64_t n_al[kNumShapes] = {0}, n_all[kNumShapes] = {0};
+        for (int g = g0; g < g1; g++) {
+            const int nh = b->region_hap_beg[g + 1] - b->region_hap_beg[g];
+            if (nh == 0) continue;
+            const int h_avg = (int)((b->hap_off[b->region_hap_beg[g + 1]] - b->hap_off[b->region_hap_beg[g]]) / nh);
+            for (int r = b->region_read_beg[g]; r < b->region_read_beg[g + 1]; r++) {
+                const int R = b->read_off[r + 1] - b->read_off[r];
+                const int sh = pick_shape(R, h_avg);
+                n_all[sh]++; n_al[sh] += is_aligned(R, sh);
+            }
+        }
+        for (int sh = 0; sh < kNumShapes; sh++) use_aligned[sh] = n_al[sh] * 10 >= n_all[sh] * 9;
+    }
+    std::vector<WarpJob> jobs_k[kSlots];
     for (int g = g0; g < g1; g++) {
-        WarpJob pending[kNumShapes];
-        int n_pending[kNumShapes];
-        for (int k = 0; k < kNumShapes; k++) n_pending[k] = 0;
+        WarpJob pending[kSlots];
+        int n_pending[kSlots];
+        for (int k = 0; k < kSlots; k++) n_pending[k] = 0;
         const int nh = b->region_hap_beg[g + 1] - b->region_hap_beg[g];
         p.max_nh = std::max(p.max_nh, nh);
         if (nh == 0) continue;
@@ -324,16 +399,20 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
         for (int r = b->region_read_beg[g]; r < b->region_read_beg[g + 1]; r++) {
             const int R = b->read_off[r + 1] - b->read_off[r];
             p.n_cells += (int64_t)R * hap_sum;
-            const int k = pick_shape(R, h_avg);
+            const int sh = pick_shape(R, h_avg);
+            // lane-aligned reads (length a multiple of K, at least K dummy rows) take the ALIGNED kernels,
+            // provided most reads of that shape do (otherwise the split only fragments the launches)
+            const bool aligned = use_aligned[sh] && is_aligned(R, sh);
+            const int k = sh + (aligned ? kNumShapes : 0);
             pending[k].read[n_pending[k]++] = r - r0;
-            if (n_pending[k] == 2 * (32 / kShapes[k].G)) flush(k);
+            if (n_pending[k] == 2 * (32 / kShapes[sh].G)) flush(k);
         }
-        for (int k = 0; k < kNumShapes; k++) if (n_pending[k]) flush(k);
+        for (int k = 0; k < kSlots; k++) if (n_pending[k]) flush(k);
     }
     for (int h = h0; h < h1; h++) p.max_H = std::max(p.max_H, b->hap_off[h + 1] - b->hap_off[h]);
     p.n_jobs = 0;
-    for (int k = 0; k < kNumShapes; k++) { p.job_beg[k] = p.n_jobs; p.n_jobs += (int)jobs_k[k].size(); }
-    p.job_beg[kNumShapes] = p.n_jobs;
+    for (int k = 0; k < kSlots; k++) { p.job_beg[k] = p.n_jobs; p.n_jobs += (int)jobs_k[k].size(); }
+    p.job_beg[kSlots] = p.n_jobs;
     {   // Haplotypes streamed per (job, chunk): as many as possible (the wavefront fills and drains
         // once per chunk), but enough (job, chunk) units to fill the chip ~8 times over, and a
         // stream that fits the per-warp shared-memory budget.
@@ -399,7 +478,7 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
         }
         std::memcpy(hp + o_haps, b->hap_bases + hb0, hap_bytes);
         WarpJob* jd = (WarpJob*)(hp + o_jobs);
-        for (int k = 0; k < kNumShapes; k++)
+        for (int k = 0; k < kSlots; k++)
             if (!jobs_k[k].empty()) std::memcpy(jd + p.job_beg[k], jobs_k[k].data(), sizeof(WarpJob) * jobs_k[k].size());
     }
 
@@ -443,32 +522,8 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
     p.h2d_bytes = in_bytes;
     if (!do_launch) return PHMM_OK;
 
-    auto launch_all = [&](bool f64) -> int {
-        for (int k = 0; k < kNumShapes; k++) {
-            const int n = p.job_beg[k + 1] - p.job_beg[k];
-            if (n == 0) continue;
-            const int per_warp = smem_bytes_per_warp(a.stream_cap, p.haps_per_job, kShapes[k]);
-            const size_t smem = (size_t)per_warp * kWarpsPerCta;
-            KernelFn fn = kernel_table().fn[f64 ? 1 : 0][exact ? 1 : 0][p.mode][k];
-            KernelArgs ak = a;
-            ak.jobs = a.jobs + p.job_beg[k];
-            ak.n_jobs = n;
-            ak.job_flag_base = p.job_beg[k];
-            ak.smem_bytes_per_warp = per_warp;
-            if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            dim3 grid((n + kWarpsPerCta - 1) / kWarpsPerCta, p.hap_chunks);
-            fn<<<grid, kWarpsPerCta * 32, smem, s.stream>>>(ak);
-            CUDA_TRY(cudaGetLastError());
-            p.launches++;
-        }
-        return PHMM_OK;
-    };
-    CUDA_TRY(cudaMemsetAsync(s.d_out.p, 0, 16, s.stream));
-    CUDA_TRY(cudaMemsetAsync(s.d_flags.p, 0, (size_t)p.n_jobs * p.hap_chunks, s.stream));
-    CUDA_TRY(cudaEventRecord(s.ev_k0, s.stream));
-    int rc = launch_all(false); if (rc) return rc;
-    rc = launch_all(true); if (rc) return rc;
-    CUDA_TRY(cudaEventRecord(s.ev_k1, s.stream));
+    int rc = launch_kernels(s, exact, false, err);
+    if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(s.h_out.p, s.d_out.p, out_bytes, cudaMemcpyDeviceToHost, s.stream));
     CUDA_TRY(cudaEventRecord(s.ev_done, s.stream));
     p.d2h_bytes = out_bytes;
@@ -540,6 +595,20 @@ int finalize_part(phmm_engine* e, DeviceCtx& dc, Slot& s, phmm_result* r, std::s
     return PHMM_OK;
 }
 
+int init_slot(Slot& s, std::string& err)
+{
+    CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    for (int i = 0; i < kAuxStreams; i++) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&s.aux[i], cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&s.ev_join[i], cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreate(&s.ev_k0));
+    CUDA_TRY(cudaEventCreate(&s.ev_k1));
+    CUDA_TRY(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+    return PHMM_OK;
+}
+
 int init_device(DeviceCtx& dc, int depth, std::string& err)
 {
     CUDA_TRY(cudaSetDevice(dc.ordinal));
@@ -558,10 +627,8 @@ int init_device(DeviceCtx& dc, int depth, std::string& err)
     CUDA_TRY(cudaMemcpy(dc.d_mm_d, T.mm_d.data(), sizeof(double) * kMmEntries, cudaMemcpyHostToDevice));
     dc.slots.resize(depth);
     for (auto& s : dc.slots) {
-        CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-        CUDA_TRY(cudaEventCreate(&s.ev_k0));
-        CUDA_TRY(cudaEventCreate(&s.ev_k1));
-        CUDA_TRY(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+        int rc = init_slot(s, err);
+        if (rc) return rc;
     }
     return PHMM_OK;
 }
@@ -570,6 +637,11 @@ void free_slot(Slot& s)
 {
     s.h_in.release(); s.h_out.release(); s.h_rescue.release();
     s.d_in.release(); s.d_out.release(); s.d_rescue.release(); s.d_flags.release();
+    for (int i = 0; i < kAuxStreams; i++) {
+        if (s.ev_join[i]) cudaEventDestroy(s.ev_join[i]);
+        if (s.aux[i]) cudaStreamDestroy(s.aux[i]);
+    }
+    if (s.ev_fork) cudaEventDestroy(s.ev_fork);
     if (s.ev_k0) cudaEventDestroy(s.ev_k0);
     if (s.ev_k1) cudaEventDestroy(s.ev_k1);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
@@ -812,10 +884,8 @@ int phmm_stage(phmm_engine* e, const phmm_batch* b, phmm_staged** out)
     dc.post([&] {
         Slot& s = st->slot;
         auto go = [&]() -> int {
-            CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-            CUDA_TRY(cudaEventCreate(&s.ev_k0));
-            CUDA_TRY(cudaEventCreate(&s.ev_k1));
-            CUDA_TRY(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+            int rc1 = init_slot(s, err);
+            if (rc1) return rc1;
             int rc2 = stage_and_launch(dc, s, b, 0, b->n_regions, 0, e->opt.exact_fp32 != 0, false, err);
             if (rc2) return rc2;
             CUDA_TRY(cudaStreamSynchronize(s.stream));
@@ -844,34 +914,17 @@ int phmm_run_staged(phmm_engine* e, phmm_staged* st, int32_t iters, float* ms_pe
         Part& p = s.part;
         const bool exact = e->opt.exact_fp32 != 0;
         auto go = [&]() -> int {
-            CUDA_TRY(cudaEventRecord(s.ev_k0, s.stream));
+            static const bool skip_rescue = getenv("PHMM_EXP_SKIP_RESCUE") != nullptr;   // timing experiments only
+            // device time of `iters` back-to-back passes: sum of the per-pass [ev_k0, ev_k1] brackets
             for (int it = 0; it < iters; it++) {
-                launches = 0;
-                CUDA_TRY(cudaMemsetAsync(s.d_out.p, 0, 16, s.stream));
-                CUDA_TRY(cudaMemsetAsync(s.d_flags.p, 0, (size_t)p.n_jobs * p.hap_chunks, s.stream));
-                static const bool skip_rescue = getenv("PHMM_EXP_SKIP_RESCUE") != nullptr;   // timing experiments only
-                for (int f64 = 0; f64 < (skip_rescue ? 1 : 2); f64++)
-                    for (int k = 0; k < kNumShapes; k++) {
-                        const int n = p.job_beg[k + 1] - p.job_beg[k];
-                        if (n == 0) continue;
-                        KernelFn fn = kernel_table().fn[f64][exact ? 1 : 0][p.mode][k];
-                        const int per_warp = smem_bytes_per_warp(s.args.stream_cap, p.haps_per_job, kShapes[k]);
-                        const size_t smem = (size_t)per_warp * kWarpsPerCta;
-                        KernelArgs ak = s.args;
-                        ak.smem_bytes_per_warp = per_warp;
-                        ak.jobs = s.args.jobs + p.job_beg[k];
-                        ak.n_jobs = n;
-                        ak.job_flag_base = p.job_beg[k];
-                        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                        dim3 grid((n + kWarpsPerCta - 1) / kWarpsPerCta, p.hap_chunks);
-                        fn<<<grid, kWarpsPerCta * 32, smem, s.stream>>>(ak);
-                        CUDA_TRY(cudaGetLastError());
-                        launches++;
-                    }
+                int rc2 = launch_kernels(s, exact, skip_rescue, err);
+                if (rc2) return rc2;
+                CUDA_TRY(cudaEventSynchronize(s.ev_k1));
+                float one = 0.f;
+                CUDA_TRY(cudaEventElapsedTime(&one, s.ev_k0, s.ev_k1));
+                ms += one;
+                launches = p.launches;
             }
-            CUDA_TRY(cudaEventRecord(s.ev_k1, s.stream));
-            CUDA_TRY(cudaEventSynchronize(s.ev_k1));
-            CUDA_TRY(cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1));
             return PHMM_OK;
         };
         rc = go();

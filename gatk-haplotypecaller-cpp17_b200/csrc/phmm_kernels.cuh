@@ -227,10 +227,16 @@ enum : int { kModeGeneral = 0, kModeConst = 1, kModeConstShared = 2 };
 #ifndef PHMM_MIN_WARPS
 #define PHMM_MIN_WARPS 16      // resident warps per SM the small-K constant-gap FP32 kernels are held to
 #endif
-template <class P, int K, int G, int MODE, bool EXACT>
+// ALIGNED: every read of the job has a length that is a multiple of K (and leaves >= K dummy rows), so
+// dummy rows fill whole lanes.  Then no row needs its own Y self-transition: all rows use the uniform
+// factor (one register-file read less per cell, K register pairs less per lane), dummy lanes may
+// compute garbage Y, and the only Y that matters -- the one handed to the first real lane -- is
+// overridden with init_Y as it is shuffled out.  Standard read lengths (100, 150, 250) qualify.
+template <class P, int K, int G, int MODE, bool EXACT, bool ALIGNED>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, (P::kIsF32 && K <= 5 && MODE != kModeGeneral) ? PHMM_MIN_WARPS / kWarpsPerCta : 1)
 forward_kernel(const KernelArgs args)
 {
+    static_assert(!ALIGNED || MODE != kModeGeneral, "ALIGNED needs batch-constant gap penalties");
     using S = typename P::S;
     using V = typename P::V;
     constexpr int NH = P::NH;
@@ -301,7 +307,7 @@ forward_kernel(const KernelArgs args)
 
         // ---- per-row setup (avx-pairhmm-template.h:83-128): transition factors in registers,
         //      priors (1 - dist on a match, dist / 3 otherwise; 0 on dummy rows) into the table ----
-        V pYY[K];                         // Y self-transition (1 on dummy rows).  In MODE 0 it is
+        V pYY[ALIGNED ? 1 : K];           // Y self-transition (1 on dummy rows).  In MODE 0 it is
                                           // also the row's X self-transition (pXX == pYY, :117,:119)
         V pMM[KP], pGAPM[KP], pMX[KP], pMY[KP];
         V pXXc = P::splat(0);             // MODE 1/2: X self-transition of every row
@@ -349,7 +355,7 @@ forward_kernel(const KernelArgs args)
                     for (int b = 0; b < 5; ++b)   // N on either side matches (:11,:21-26)
                         reinterpret_cast<S*>(reinterpret_cast<uint8_t*>(my_tab) + b * SUBT + k * 8)[hf] =
                             (rc == 4 || b == 4 || rc == b) ? mat : mis;
-                    P::set(pYY[k], hf, yy);
+                    if (!ALIGNED) P::set(pYY[k], hf, yy);
                     if (!CONSTG) {
                         P::set(pMM[k], hf, mm_);
                         P::set(pGAPM[k], hf, gapm);
@@ -363,6 +369,9 @@ forward_kernel(const KernelArgs args)
         // bottom row back (shfl_up at the group edge), which these two zeros annihilate.
         const V pMX0 = (l == 0) ? P::splat(0) : pMX[0];
         const V pXX0 = (l == 0) ? P::splat(0) : (CONSTG ? pXXc : pYY[0]);
+        bool dummy_lane[NH];              // ALIGNED: this lane holds only dummy rows of packed read hf
+#pragma unroll
+        for (int hf = 0; hf < NH; ++hf) dummy_lane[hf] = l * K < pad[hf];
 
         // ---- haplotypes of this chunk, streamed back to back through ONE wavefront ----
         // Shared memory (per warp): a byte stream
@@ -416,7 +425,8 @@ forward_kernel(const KernelArgs args)
             }
             sumM = P::splat(0); sumX = P::splat(0);
         };
-        reset_state(s_inity[0]);
+        S inity_cur = s_inity[0];
+        reset_state(inity_cur);
         // values of the row above this lane's first row: at the current column (in*) and at the
         // previous column (dg*).  Lane 0 never uses them (its row 0 is a dummy row with zero
         // priors, pMX0 = pXX0 = 0 and pYY = 1).
@@ -454,7 +464,8 @@ forward_kernel(const KernelArgs args)
             for (int k = 0; k < K; ++k) {
                 const int kk = CONSTG ? 0 : k;
                 const V yv = SHARED ? Pm[k] : P::mul(M[k], pMY[kk]);
-                Y[k] = EXACT ? P::addx(yv, P::mul(Y[k], pYY[k])) : P::fma(Y[k], pYY[k], yv);
+                const V cYY = ALIGNED ? pXXc : pYY[ALIGNED ? 0 : k];
+                Y[k] = EXACT ? P::addx(yv, P::mul(Y[k], cYY)) : P::fma(Y[k], cYY, yv);
             }
             // Phase B: M = t0 * prior (:152-158, :188)
 #pragma unroll
@@ -466,7 +477,7 @@ forward_kernel(const KernelArgs args)
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const int kk = CONSTG ? 0 : k;
-                const V cXX = (k == 0) ? pXX0 : (CONSTG ? pXXc : pYY[k]);
+                const V cXX = (k == 0) ? pXX0 : (CONSTG ? pXXc : pYY[ALIGNED ? 0 : k]);
                 const V uX = k ? X[k - 1] : inX;            // (row-1, c)
                 V um;                                       // M(row-1, c) * pMX(row)
                 if (k == 0) um = P::mul(inM, pMX0);
@@ -480,15 +491,17 @@ forward_kernel(const KernelArgs args)
         // hand the bottom row to the lane below
         auto rotate = [&]() {
             dgM = inM; dgX = inX; dgY = inY;
+            // ALIGNED: a dummy lane's Y is garbage; what the lane below must see is row 0's init_Y
+            const V outY = ALIGNED ? P::sel(dummy_lane[0], dummy_lane[NH - 1], P::splat(inity_cur), Y[K - 1]) : Y[K - 1];
             if (kSkew == 2) {
                 inM = qM; inX = qX; inY = qY;
                 qM = P::shfl_up(M[K - 1], G);
                 qX = P::shfl_up(X[K - 1], G);
-                qY = P::shfl_up(Y[K - 1], G);
+                qY = P::shfl_up(outY, G);
             } else {
                 inM = P::shfl_up(M[K - 1], G);
                 inX = P::shfl_up(X[K - 1], G);
-                inY = P::shfl_up(Y[K - 1], G);
+                inY = P::shfl_up(outY, G);
             }
         };
         // a haplotype ends for this lane
@@ -513,7 +526,8 @@ forward_kernel(const KernelArgs args)
                 }
             }
             ++jcur;
-            reset_state(s_inity[min(jcur, n - 1)]);
+            inity_cur = s_inity[min(jcur, n - 1)];
+            reset_state(inity_cur);
         };
 
         // shared address of this lane's byte at step t is bp + t

@@ -19,8 +19,9 @@ constexpr Shape kShapes[kNumShapes] = {
 constexpr int kMaxReadLenCompiled = 32 * 8 - 1;   // 255
 
 constexpr int kNumModes = 3;
-// tab[mode][shape]
-using KernelTab = KernelFn[kNumModes][kNumShapes];
+// tab[mode][aligned][shape]; aligned = every read length of the job is a multiple of K (constant-gap
+// modes only; the general mode has no aligned variant and its [1] row repeats [0])
+using KernelTab = KernelFn[kNumModes][2][kNumShapes];
 
 // One translation unit per (precision, exact) keeps nvcc parallel; each fills its slice.
 void register_f32_fast(KernelTab& tab);
@@ -28,32 +29,116 @@ void register_f32_exact(KernelTab& tab);
 void register_f64_fast(KernelTab& tab);
 void register_f64_exact(KernelTab& tab);
 
-#define PHMM_REGISTER_MODE(POLICY, EXACT, MODE)                                                  \
-    do {                                                                                         \
-        tab[MODE][0]  = forward_kernel<POLICY, 1, 32, MODE, EXACT>;                              \
-        tab[MODE][1]  = forward_kernel<POLICY, 2, 32, MODE, EXACT>;                              \
-        tab[MODE][2]  = forward_kernel<POLICY, 3, 32, MODE, EXACT>;                              \
-        tab[MODE][3]  = forward_kernel<POLICY, 4, 32, MODE, EXACT>;                              \
-        tab[MODE][4]  = forward_kernel<POLICY, 5, 32, MODE, EXACT>;                              \
-        tab[MODE][5]  = forward_kernel<POLICY, 6, 32, MODE, EXACT>;                              \
-        tab[MODE][6]  = forward_kernel<POLICY, 7, 32, MODE, EXACT>;                              \
-        tab[MODE][7]  = forward_kernel<POLICY, 8, 32, MODE, EXACT>;                              \
-        tab[MODE][8]  = forward_kernel<POLICY, 1, 16, MODE, EXACT>;                              \
-        tab[MODE][9]  = forward_kernel<POLICY, 2, 16, MODE, EXACT>;                              \
-        tab[MODE][10] = forward_kernel<POLICY, 3, 16, MODE, EXACT>;                              \
-        tab[MODE][11] = forward_kernel<POLICY, 4, 16, MODE, EXACT>;                              \
-        tab[MODE][12] = forward_kernel<POLICY, 5, 16, MODE, EXACT>;                              \
-        tab[MODE][13] = forward_kernel<POLICY, 6, 16, MODE, EXACT>;                              \
-        tab[MODE][14] = forward_kernel<POLICY, 7, 16, MODE, EXACT>;                              \
-        tab[MODE][15] = forward_kernel<POLICY, 8, 16, MODE, EXACT>;                              \
-        tab[MODE][16] = forward_kernel<POLICY, 9, 16, MODE, EXACT>;                              \
-        tab[MODE][17] = forward_kernel<POLICY, 10, 16, MODE, EXACT>;                             \
-    } while (0)
 #define PHMM_REGISTER_ALL(POLICY, EXACT)                                                         \
     do {                                                                                         \
-        PHMM_REGISTER_MODE(POLICY, EXACT, 0);                                                    \
-        PHMM_REGISTER_MODE(POLICY, EXACT, 1);                                                    \
-        PHMM_REGISTER_MODE(POLICY, EXACT, 2);                                                    \
+        tab[0][0][0] = forward_kernel<POLICY, 1, 32, 0, EXACT, false>;                           \
+        tab[0][0][1] = forward_kernel<POLICY, 2, 32, 0, EXACT, false>;                           \
+        tab[0][0][2] = forward_kernel<POLICY, 3, 32, 0, EXACT, false>;                           \
+        tab[0][0][3] = forward_kernel<POLICY, 4, 32, 0, EXACT, false>;                           \
+        tab[0][0][4] = forward_kernel<POLICY, 5, 32, 0, EXACT, false>;                           \
+        tab[0][0][5] = forward_kernel<POLICY, 6, 32, 0, EXACT, false>;                           \
+        tab[0][0][6] = forward_kernel<POLICY, 7, 32, 0, EXACT, false>;                           \
+        tab[0][0][7] = forward_kernel<POLICY, 8, 32, 0, EXACT, false>;                           \
+        tab[0][0][8] = forward_kernel<POLICY, 1, 16, 0, EXACT, false>;                           \
+        tab[0][0][9] = forward_kernel<POLICY, 2, 16, 0, EXACT, false>;                           \
+        tab[0][0][10] = forward_kernel<POLICY, 3, 16, 0, EXACT, false>;                          \
+        tab[0][0][11] = forward_kernel<POLICY, 4, 16, 0, EXACT, false>;                          \
+        tab[0][0][12] = forward_kernel<POLICY, 5, 16, 0, EXACT, false>;                          \
+        tab[0][0][13] = forward_kernel<POLICY, 6, 16, 0, EXACT, false>;                          \
+        tab[0][0][14] = forward_kernel<POLICY, 7, 16, 0, EXACT, false>;                          \
+        tab[0][0][15] = forward_kernel<POLICY, 8, 16, 0, EXACT, false>;                          \
+        tab[0][0][16] = forward_kernel<POLICY, 9, 16, 0, EXACT, false>;                          \
+        tab[0][0][17] = forward_kernel<POLICY, 10, 16, 0, EXACT, false>;                         \
+        tab[0][1][0] = forward_kernel<POLICY, 1, 32, 0, EXACT, false>;                           \
+        tab[0][1][1] = forward_kernel<POLICY, 2, 32, 0, EXACT, false>;                           \
+        tab[0][1][2] = forward_kernel<POLICY, 3, 32, 0, EXACT, false>;                           \
+        tab[0][1][3] = forward_kernel<POLICY, 4, 32, 0, EXACT, false>;                           \
+        tab[0][1][4] = forward_kernel<POLICY, 5, 32, 0, EXACT, false>;                           \
+        tab[0][1][5] = forward_kernel<POLICY, 6, 32, 0, EXACT, false>;                           \
+        tab[0][1][6] = forward_kernel<POLICY, 7, 32, 0, EXACT, false>;                           \
+        tab[0][1][7] = forward_kernel<POLICY, 8, 32, 0, EXACT, false>;                           \
+        tab[0][1][8] = forward_kernel<POLICY, 1, 16, 0, EXACT, false>;                           \
+        tab[0][1][9] = forward_kernel<POLICY, 2, 16, 0, EXACT, false>;                           \
+        tab[0][1][10] = forward_kernel<POLICY, 3, 16, 0, EXACT, false>;                          \
+        tab[0][1][11] = forward_kernel<POLICY, 4, 16, 0, EXACT, false>;                          \
+        tab[0][1][12] = forward_kernel<POLICY, 5, 16, 0, EXACT, false>;                          \
+        tab[0][1][13] = forward_kernel<POLICY, 6, 16, 0, EXACT, false>;                          \
+        tab[0][1][14] = forward_kernel<POLICY, 7, 16, 0, EXACT, false>;                          \
+        tab[0][1][15] = forward_kernel<POLICY, 8, 16, 0, EXACT, false>;                          \
+        tab[0][1][16] = forward_kernel<POLICY, 9, 16, 0, EXACT, false>;                          \
+        tab[0][1][17] = forward_kernel<POLICY, 10, 16, 0, EXACT, false>;                         \
+        tab[1][0][0] = forward_kernel<POLICY, 1, 32, 1, EXACT, false>;                           \
+        tab[1][0][1] = forward_kernel<POLICY, 2, 32, 1, EXACT, false>;                           \
+        tab[1][0][2] = forward_kernel<POLICY, 3, 32, 1, EXACT, false>;                           \
+        tab[1][0][3] = forward_kernel<POLICY, 4, 32, 1, EXACT, false>;                           \
+        tab[1][0][4] = forward_kernel<POLICY, 5, 32, 1, EXACT, false>;                           \
+        tab[1][0][5] = forward_kernel<POLICY, 6, 32, 1, EXACT, false>;                           \
+        tab[1][0][6] = forward_kernel<POLICY, 7, 32, 1, EXACT, false>;                           \
+        tab[1][0][7] = forward_kernel<POLICY, 8, 32, 1, EXACT, false>;                           \
+        tab[1][0][8] = forward_kernel<POLICY, 1, 16, 1, EXACT, false>;                           \
+        tab[1][0][9] = forward_kernel<POLICY, 2, 16, 1, EXACT, false>;                           \
+        tab[1][0][10] = forward_kernel<POLICY, 3, 16, 1, EXACT, false>;                          \
+        tab[1][0][11] = forward_kernel<POLICY, 4, 16, 1, EXACT, false>;                          \
+        tab[1][0][12] = forward_kernel<POLICY, 5, 16, 1, EXACT, false>;                          \
+        tab[1][0][13] = forward_kernel<POLICY, 6, 16, 1, EXACT, false>;                          \
+        tab[1][0][14] = forward_kernel<POLICY, 7, 16, 1, EXACT, false>;                          \
+        tab[1][0][15] = forward_kernel<POLICY, 8, 16, 1, EXACT, false>;                          \
+        tab[1][0][16] = forward_kernel<POLICY, 9, 16, 1, EXACT, false>;                          \
+        tab[1][0][17] = forward_kernel<POLICY, 10, 16, 1, EXACT, false>;                         \
+        tab[1][1][0] = forward_kernel<POLICY, 1, 32, 1, EXACT, true>;                            \
+        tab[1][1][1] = forward_kernel<POLICY, 2, 32, 1, EXACT, true>;                            \
+        tab[1][1][2] = forward_kernel<POLICY, 3, 32, 1, EXACT, true>;                            \
+        tab[1][1][3] = forward_kernel<POLICY, 4, 32, 1, EXACT, true>;                            \
+        tab[1][1][4] = forward_kernel<POLICY, 5, 32, 1, EXACT, true>;                            \
+        tab[1][1][5] = forward_kernel<POLICY, 6, 32, 1, EXACT, true>;                            \
+        tab[1][1][6] = forward_kernel<POLICY, 7, 32, 1, EXACT, true>;                            \
+        tab[1][1][7] = forward_kernel<POLICY, 8, 32, 1, EXACT, true>;                            \
+        tab[1][1][8] = forward_kernel<POLICY, 1, 16, 1, EXACT, true>;                            \
+        tab[1][1][9] = forward_kernel<POLICY, 2, 16, 1, EXACT, true>;                            \
+        tab[1][1][10] = forward_kernel<POLICY, 3, 16, 1, EXACT, true>;                           \
+        tab[1][1][11] = forward_kernel<POLICY, 4, 16, 1, EXACT, true>;                           \
+        tab[1][1][12] = forward_kernel<POLICY, 5, 16, 1, EXACT, true>;                           \
+        tab[1][1][13] = forward_kernel<POLICY, 6, 16, 1, EXACT, true>;                           \
+        tab[1][1][14] = forward_kernel<POLICY, 7, 16, 1, EXACT, true>;                           \
+        tab[1][1][15] = forward_kernel<POLICY, 8, 16, 1, EXACT, true>;                           \
+        tab[1][1][16] = forward_kernel<POLICY, 9, 16, 1, EXACT, true>;                           \
+        tab[1][1][17] = forward_kernel<POLICY, 10, 16, 1, EXACT, true>;                          \
+        tab[2][0][0] = forward_kernel<POLICY, 1, 32, 2, EXACT, false>;                           \
+        tab[2][0][1] = forward_kernel<POLICY, 2, 32, 2, EXACT, false>;                           \
+        tab[2][0][2] = forward_kernel<POLICY, 3, 32, 2, EXACT, false>;                           \
+        tab[2][0][3] = forward_kernel<POLICY, 4, 32, 2, EXACT, false>;                           \
+        tab[2][0][4] = forward_kernel<POLICY, 5, 32, 2, EXACT, false>;                           \
+        tab[2][0][5] = forward_kernel<POLICY, 6, 32, 2, EXACT, false>;                           \
+        tab[2][0][6] = forward_kernel<POLICY, 7, 32, 2, EXACT, false>;                           \
+        tab[2][0][7] = forward_kernel<POLICY, 8, 32, 2, EXACT, false>;                           \
+        tab[2][0][8] = forward_kernel<POLICY, 1, 16, 2, EXACT, false>;                           \
+        tab[2][0][9] = forward_kernel<POLICY, 2, 16, 2, EXACT, false>;                           \
+        tab[2][0][10] = forward_kernel<POLICY, 3, 16, 2, EXACT, false>;                          \
+        tab[2][0][11] = forward_kernel<POLICY, 4, 16, 2, EXACT, false>;                          \
+        tab[2][0][12] = forward_kernel<POLICY, 5, 16, 2, EXACT, false>;                          \
+        tab[2][0][13] = forward_kernel<POLICY, 6, 16, 2, EXACT, false>;                          \
+        tab[2][0][14] = forward_kernel<POLICY, 7, 16, 2, EXACT, false>;                          \
+        tab[2][0][15] = forward_kernel<POLICY, 8, 16, 2, EXACT, false>;                          \
+        tab[2][0][16] = forward_kernel<POLICY, 9, 16, 2, EXACT, false>;                          \
+        tab[2][0][17] = forward_kernel<POLICY, 10, 16, 2, EXACT, false>;                         \
+        tab[2][1][0] = forward_kernel<POLICY, 1, 32, 2, EXACT, true>;                            \
+        tab[2][1][1] = forward_kernel<POLICY, 2, 32, 2, EXACT, true>;                            \
+        tab[2][1][2] = forward_kernel<POLICY, 3, 32, 2, EXACT, true>;                            \
+        tab[2][1][3] = forward_kernel<POLICY, 4, 32, 2, EXACT, true>;                            \
+        tab[2][1][4] = forward_kernel<POLICY, 5, 32, 2, EXACT, true>;                            \
+        tab[2][1][5] = forward_kernel<POLICY, 6, 32, 2, EXACT, true>;                            \
+        tab[2][1][6] = forward_kernel<POLICY, 7, 32, 2, EXACT, true>;                            \
+        tab[2][1][7] = forward_kernel<POLICY, 8, 32, 2, EXACT, true>;                            \
+        tab[2][1][8] = forward_kernel<POLICY, 1, 16, 2, EXACT, true>;                            \
+        tab[2][1][9] = forward_kernel<POLICY, 2, 16, 2, EXACT, true>;                            \
+        tab[2][1][10] = forward_kernel<POLICY, 3, 16, 2, EXACT, true>;                           \
+        tab[2][1][11] = forward_kernel<POLICY, 4, 16, 2, EXACT, true>;                           \
+        tab[2][1][12] = forward_kernel<POLICY, 5, 16, 2, EXACT, true>;                           \
+        tab[2][1][13] = forward_kernel<POLICY, 6, 16, 2, EXACT, true>;                           \
+        tab[2][1][14] = forward_kernel<POLICY, 7, 16, 2, EXACT, true>;                           \
+        tab[2][1][15] = forward_kernel<POLICY, 8, 16, 2, EXACT, true>;                           \
+        tab[2][1][16] = forward_kernel<POLICY, 9, 16, 2, EXACT, true>;                           \
+        tab[2][1][17] = forward_kernel<POLICY, 10, 16, 2, EXACT, true>;                          \
     } while (0)
 
 }  // namespace phmm
