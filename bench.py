@@ -12,7 +12,7 @@ over one such batch.  GCUPS = sum over pairs of read_len x hap_len / seconds / 1
   value      inputs already resident in HBM (phmm_stage), kernels only, CUDA events on the launching
              stream (inside the C library), max over ranks, summed over ranks' cells.
   e2e        the same batches through the C ABI with HOST buffers (phmm_submit / phmm_wait, pipeline
-             depth 2): pack to pinned staging + H2D + kernels + D2H + host log10, wall clock.
+             4 batches in flight): pack to pinned staging + H2D + kernels + D2H + host log10, wall clock.
   roofline   FP32 CUDA-core issue roofline of SURVEY.md section 8(d): SMs x 128 lanes x f_SM / 8
              FP32-pipe instructions per cell (NOT HBM: 7.6e-4 B/cell); `peak` uses the max SM clock
              of MEASURED_PEAKS.json, `peak_at_clock` the median clock sampled during the run.
@@ -252,7 +252,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    eng = pkg.PairHMMEngine(devices=[local], pipeline_depth=2, host_threads=4)
+    DEPTH = 4                                                      # batches in flight on the e2e path
+    eng = pkg.PairHMMEngine(devices=[local], pipeline_depth=DEPTH, host_threads=4)
     # distinct batches per rank (weak scaling: every GPU gets its own `regions` regions per step)
     batches = [pkg.synth.s3(args.regions, seed=1003 + 1000 * rank + i) for i in range(args.nbatch)]
     cells_per_step = batches[0].n_cells
@@ -286,18 +287,20 @@ def main():
     checksum = float(np.sum(res.log10[np.isfinite(res.log10)]))
 
     # ---- e2e: host buffers through phmm_submit / phmm_wait (pack + H2D + kernels + D2H + log10) ----
+    from collections import deque
     results = [pkg.Result(b.n_pairs, want_raw=False) for b in batches[:2]]
-    for w in range(args.warmup):
+    for w in range(max(args.warmup, DEPTH)):                      # also grows every slot's buffers
         eng.compute(batches[w % args.nbatch], want_raw=False)
     barrier()
     t0 = time.perf_counter()
-    tk = eng.submit(batches[0])
+    inflight, submitted, done = deque(), 0, 0
     h2d = d2h = 0
-    for s in range(1, args.steps + 1):
-        nxt = eng.submit(batches[s % args.nbatch]) if s < args.steps else None
-        r = eng.wait(tk, result=results[s % 2])
+    while done < args.steps:                                      # every step: H2D of its inputs, D2H of its results
+        while len(inflight) < DEPTH and submitted < args.steps:
+            inflight.append(eng.submit(batches[submitted % args.nbatch])); submitted += 1
+        r = eng.wait(inflight.popleft(), result=results[done % 2])
         h2d += r.stats["h2d_bytes"]; d2h += r.stats["d2h_bytes"]
-        tk = nxt
+        done += 1
     barrier()
     e2e_s = time.perf_counter() - t0
     e2e_s_max = max_over_ranks(e2e_s, world)
@@ -327,7 +330,7 @@ def main():
                        "parallelism": f"regions sharded over {world} GPU(s), no collective on the data path"},
             "e2e": {"value": round(e2e, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d / args.steps),
                     "d2h_bytes_per_step": int(d2h / args.steps),
-                    "path": "phmm_submit/phmm_wait with host buffers, pipeline depth 2, 4 finalize threads"},
+                    "path": f"phmm_submit/phmm_wait with host buffers, {DEPTH} batches in flight, 4 finalize threads"},
             "gpu_launches": launches,
             "roofline": {"bound": "fp32_cuda_core", "achieved": round(per_gpu, 1), "peak": round(peak, 1), "unit": UNIT,
                          "frac": round(per_gpu / peak, 4), "traffic": None,

@@ -66,7 +66,18 @@ inline int smem_bytes_per_warp(int stream_cap, int haps_per_job, Shape sh)
 // dummy row on top).  Cost model (warp cycles per scored pair): a step costs ~15 FP32-pipe cycles
 // per row plus ~10 of per-step work; a haplotype takes H + G - 1 steps; a warp holds 32/G groups.
 // PHMM_FORCE_GROUP=16|32 restricts the choice (benchmarking aid).
+inline int pick_shape_uncached(int R, int H);
 inline int pick_shape(int R, int H)
+{
+    // reads of one region share H and mostly R: remember the answers for the current H
+    thread_local int cached_h = -1;
+    thread_local int16_t cache[kMaxReadLenCompiled + 2];
+    if (R < 1 || R > kMaxReadLenCompiled) return pick_shape_uncached(R, H);
+    if (H != cached_h) { for (auto& c : cache) c = -2; cached_h = H; }
+    if (cache[R] == -2) cache[R] = (int16_t)pick_shape_uncached(R, H);
+    return cache[R];
+}
+inline int pick_shape_uncached(int R, int H)
 {
     static const int force = [] { const char* s = getenv("PHMM_FORCE_GROUP"); return s ? atoi(s) : 0; }();
     int best = -1; double best_cost = 0;
