@@ -194,3 +194,76 @@ def random_small(seed, n_regions=3, max_reads=9, max_haps=5, max_read_len=70, ma
             gc.append((33 + rng.integers(5, 25, rl)).astype(np.uint8))
         regions.append((reads, quals, haps, gi, gd, gc) if general_gaps else (reads, quals, haps))
     return _batch_cls().from_regions(regions)
+
+
+def chrm_like(prefix, length=16569, seed=1001, read_len=150, density=0.30, snp_every=350, indel_every=1400,
+              contig="chrM"):
+    """BASELINE config 1 stand-in (S1): the reference's own chrM files are not shipped, so this writes a
+    synthetic chrM-like `prefix.fa` + `prefix.sam` for the end-to-end harness (oracle/hc_e2e.cpp):
+    a random 16 569 bp contig, a truth set of SNPs and small indels (het or hom) carried by two phased
+    haplotypes, and 150 bp reads with AT MOST ONE READ PER START POSITION (the reference picks one read
+    per start with std::random_device, haplotypecaller.hpp:44-50; one candidate makes the draw forced).
+    MAPQ 60, RNEXT '=', proper CIGARs for reads spanning indels, 0.5 % substitutions, Q in [25,40].
+    Returns the truth list [(pos0, kind, alt, genotype)]."""
+    rng = np.random.default_rng(seed)
+    ref = ACGT[rng.integers(0, 4, length)]
+    truth = []                       # spaced so that the variants do not interact
+    pos = 200
+    while pos < length - 400:
+        kind = "snp"
+        if rng.random() < snp_every / indel_every:
+            kind = "ins" if rng.random() < 0.5 else "del"
+        gt = "hom" if rng.random() < 0.3 else "het"
+        if kind == "snp":
+            alt = ACGT[(int(np.where(ACGT == ref[pos])[0][0]) + int(rng.integers(1, 4))) % 4]
+            truth.append((pos, "snp", bytes([alt]), gt))
+        elif kind == "ins":
+            truth.append((pos, "ins", ACGT[rng.integers(0, 4, int(rng.integers(1, 4)))].tobytes(), gt))
+        else:
+            truth.append((pos, "del", int(rng.integers(1, 4)), gt))
+        pos += int(rng.integers(snp_every // 2, snp_every * 3 // 2))
+    with open(prefix + ".fa", "w") as f:
+        f.write(f">{contig}\n")
+        s = ref.tobytes().decode()
+        for i in range(0, length, 60):
+            f.write(s[i:i + 60] + "\n")
+
+    def make_read(start, hap):
+        """Walk the reference from `start`, applying the variants this haplotype carries."""
+        seq, cigar, p, n_m = [], [], start, 0
+        vi = {v[0]: v for v in truth if v[3] == "hom" or hap == 1}
+        while len(seq) < read_len and p < length:
+            v = vi.get(p)
+            if v is None or v[1] == "snp":
+                seq.append(v[2][0] if v is not None else ref[p]); n_m += 1; p += 1
+            elif v[1] == "ins":                       # anchor base, then the inserted bases
+                seq.append(ref[p]); n_m += 1; p += 1
+                ins = list(v[2])[: read_len - len(seq)]
+                if ins:
+                    cigar.append(f"{n_m}M{len(ins)}I"); n_m = 0; seq += ins
+            else:                                     # anchor base, then skip the deleted bases
+                seq.append(ref[p]); n_m += 1; p += 1
+                if len(seq) < read_len and p + v[2] < length:
+                    cigar.append(f"{n_m}M{v[2]}D"); n_m = 0; p += v[2]
+        if n_m:
+            cigar.append(f"{n_m}M")
+        if cigar and cigar[-1].endswith(("I", "D")):   # never end on an indel
+            return None
+        return np.array(seq, np.uint8), "".join(cigar)
+
+    n = 0
+    with open(prefix + ".sam", "w") as f:
+        f.write(f"@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:{contig}\tLN:{length}\n")
+        for start in range(0, length - read_len - 8):
+            if rng.random() > density:
+                continue
+            r = make_read(start, int(rng.integers(0, 2)))
+            if r is None:
+                continue
+            seq, cigar = r
+            sub = rng.random(len(seq)) < 0.005
+            seq = seq.copy(); seq[sub] = ACGT[rng.integers(0, 4, int(sub.sum()))]
+            qual = (33 + rng.integers(25, 41, len(seq))).astype(np.uint8)
+            f.write(f"r{n}\t0\t{contig}\t{start + 1}\t60\t{cigar}\t=\t{start + 1}\t0\t{seq.tobytes().decode()}\t{qual.tobytes().decode()}\n")
+            n += 1
+    return truth

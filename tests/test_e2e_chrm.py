@@ -1,0 +1,59 @@
+"""chrM-style END-TO-END parity (BASELINE config 1 / SURVEY.md section 8f-1): the reference's whole
+driver (FASTA+SAM load, windowing, filters, clipping, local assembly, PairHMM, genotyping, VCF),
+compiled unmodified from /root/reference with a Boost.Graph shim (oracle/hc_e2e.cpp), once around
+hc::IntelPairHMM and once around hc::B200PairHMM.  Input: a synthetic chrM-like contig with at most one
+read per start position (the reference's only source of non-determinism), regenerated from a seed.
+
+  CPU : the reference-engine run reproduces the committed golden VCF;
+  GPU : the B200-engine run writes a BIT-IDENTICAL VCF file; wall times of both are printed.
+"""
+import os
+import subprocess
+import time
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_EXE = os.path.join(ROOT, "oracle", "_ref", "hc_e2e_ref")
+B200_EXE = os.path.join(ROOT, "oracle", "_ref", "hc_e2e_b200")
+GOLDEN = os.path.join(ROOT, "tests", "golden", "chrm_like.ref.vcf")
+needs = pytest.mark.skipif(not (os.path.exists(REF_EXE) and os.path.exists(B200_EXE)),
+                           reason="oracle/_ref/hc_e2e_* not built (needs /root/reference at build time)")
+
+
+def _run(exe, prefix, out):
+    t0 = time.perf_counter()
+    r = subprocess.run([exe, "-I", prefix + ".sam", "-R", prefix + ".fa", "-O", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return time.perf_counter() - t0, r.stderr.strip().splitlines()[-1]
+
+
+@pytest.fixture(scope="module")
+def data(tmp_path_factory, pkg):
+    prefix = str(tmp_path_factory.mktemp("chrm") / "chrm_like")
+    truth = pkg.synth.chrm_like(prefix)
+    return prefix, truth
+
+
+@needs
+def test_reference_engine_end_to_end_matches_golden(data, tmp_path):
+    prefix, truth = data
+    out = str(tmp_path / "ref.vcf")
+    _run(REF_EXE, prefix, out)
+    got = open(out).read()
+    assert got == open(GOLDEN).read()
+    called = {int(l.split("\t")[1]) for l in got.splitlines() if not l.startswith("#")}
+    snps = [p for p, kind, _, _ in truth if kind == "snp"]
+    assert sum((p + 1) in called for p in snps) >= 0.9 * len(snps)      # the pipeline really calls the truth
+
+
+@pytest.mark.gpu
+@needs
+def test_b200_engine_end_to_end_vcf_is_bit_identical(data, tmp_path):
+    prefix, _ = data
+    ref_out, b200_out = str(tmp_path / "ref.vcf"), str(tmp_path / "b200.vcf")
+    t_ref, log_ref = _run(REF_EXE, prefix, ref_out)
+    t_b200, log_b200 = _run(B200_EXE, prefix, b200_out)
+    print(f"\nchrM-like e2e wall: reference engine {t_ref:.2f} s ({log_ref}) | B200 engine {t_b200:.2f} s ({log_b200})")
+    assert open(b200_out, "rb").read() == open(ref_out, "rb").read()
+    assert open(b200_out).read() == open(GOLDEN).read()
