@@ -56,9 +56,13 @@ constexpr int kWarpsPerCta = PHMM_WARPS_PER_CTA;
 constexpr int kMaxJobReads = 8;          // reads per warp job: 2 per lane group, up to 4 groups (G = 8)
 constexpr float kMinAccepted = 1e-28f;   // pairhmm/native/pairhmm_common.h:16
 // Lane l+1 runs kSkew columns behind lane l.  With 2, the bottom row a lane shuffles down at the end
-// of a step is not consumed until a whole step later, so the shuffle latency never sits on the
-// X-chain critical path (measured: the shuffles cost 17% at K=10 with a skew of 1).
-constexpr int kSkew = 2;
+// of a step is not consumed until a whole step later (shuffle latency off the X-chain critical path).
+// Measured on the final kernel: no gain (the other warps hide that latency) while the straddling
+// zone between two haplotypes doubles; 1 is 2-7% faster on every shape, so 1 is the default.
+#ifndef PHMM_SKEW
+#define PHMM_SKEW 1
+#endif
+constexpr int kSkew = PHMM_SKEW;
 
 struct WarpJob {
     int32_t region;
