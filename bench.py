@@ -314,6 +314,14 @@ def main():
     all_sums = gather_results(np.array([checksum]), rank, world, rank, world)
 
     if rank == 0:
+        # DRAM traffic of the dominant kernel, per launch, from the committed `ncu --set full` capture
+        # (profiles/r01_ncu_bench_forward_kernel.txt: a 64-region launch), scaled to this launch's regions
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = int((tj["dram_read_bytes"] + tj["dram_write_bytes"]) * args.regions / tj["regions"])
+        except Exception:
+            pass
         peak = sms * SM_LANES * (sm_max_mhz * 1e6) / INSTR_PER_CELL / 1e9
         mhz = clocks.get("sm_mhz") or sm_max_mhz
         peak_clk = sms * SM_LANES * (mhz * 1e6) / INSTR_PER_CELL / 1e9
@@ -333,11 +341,12 @@ def main():
                     "path": f"phmm_submit/phmm_wait with host buffers, {DEPTH} batches in flight, 4 finalize threads"},
             "gpu_launches": launches,
             "roofline": {"bound": "fp32_cuda_core", "achieved": round(per_gpu, 1), "peak": round(peak, 1), "unit": UNIT,
-                         "frac": round(per_gpu / peak, 4), "traffic": None,
+                         "frac": round(per_gpu / peak, 4), "traffic": traffic,
+                         "algorithmic_bytes": in_bytes + out_bytes,
                          "peak_def": f"{sms} SMs x {SM_LANES} FP32 lanes x {sm_max_mhz:.0f} MHz / {INSTR_PER_CELL} FP32-pipe instr per cell "
                                      "(max SM clock of MEASURED_PEAKS.json; not HBM-bound: 7.6e-4 B/cell)",
                          "peak_at_clock": round(peak_clk, 1), "frac_at_clock": round(per_gpu / peak_clk, 4),
-                         "kernel": "forward_kernel<PolicyF32x2, K=10, G=16, MODE=2> (+ FP64 rescue) per step, CUDA events in-library",
+                         "kernel": "forward_kernel<PolicyF32x2, K=10, G=16, MODE=2, ALIGNED> (+ its FP64 rescue pass) per step, CUDA events in-library",
                          "hbm_staging_gbs": round((in_bytes + out_bytes) / (dev_ms / args.steps * 1e-3) / 1e9, 2)},
             "clocks": clocks,
             "wall_ms_kernel_region": round(wall_ms, 2),
