@@ -320,8 +320,13 @@ int launch_kernels(Slot& s, bool exact, bool skip_rescue, std::string& err)
         ak.job_flag_base = p.job_beg[k];
         ak.smem_bytes_per_warp = per_warp;
         dim3 grid((n + kWarpsPerCta - 1) / kWarpsPerCta, p.hap_chunks);
-        for (int f64 = 0; f64 < (skip_rescue ? 1 : 2); f64++) {      // the FP64 redo follows its FP32 pass
-            KernelFn fn = kernel_table().fn[f64][exact ? 1 : 0][p.mode][k / kNumShapes][k % kNumShapes];
+        // tier 1 FP32, tier 2 its FP64 redo, tier 3 (fast engine only) the flush-exact FP64 redo of pairs that
+        // ended within reach of the denormal range -- the EXACT FP64 kernel; it finds no flagged work and
+        // exits at once in all but pathological batches
+        const int n_tiers = skip_rescue ? 1 : (exact ? 2 : 3);
+        for (int tier = 1; tier <= n_tiers; tier++) {
+            KernelFn fn = kernel_table().fn[tier >= 2][(exact || tier == 3) ? 1 : 0][p.mode][k / kNumShapes][k % kNumShapes];
+            ak.tier = tier;
             if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             fn<<<grid, kWarpsPerCta * 32, smem, st>>>(ak);
             CUDA_TRY(cudaGetLastError());
@@ -574,7 +579,7 @@ int finalize_part(phmm_engine* e, DeviceCtx& dc, Slot& s, phmm_result* r, std::s
             const float f = raw32[i];
             if (f < kMinAccepted) { nr++; out[i] = std::nan(""); }
             else out[i] = (double)(log10f(f) - log10_init_f);       // float subtraction, :142
-            if (o32) o32[i] = f;
+            if (o32) o32[i] = std::fabs(f);     // the sign bit only marks pairs the flush-exact FP64 tier redid
             if (o64) o64[i] = 0.0;
             if (ores) ores[i] = 0;
         }

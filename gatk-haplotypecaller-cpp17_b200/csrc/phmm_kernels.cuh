@@ -55,6 +55,14 @@ namespace phmm {
 constexpr int kWarpsPerCta = PHMM_WARPS_PER_CTA;
 constexpr int kMaxJobReads = 8;          // reads per warp job: 2 per lane group, up to 4 groups (G = 8)
 constexpr float kMinAccepted = 1e-28f;   // pairhmm/native/pairhmm_common.h:16
+// Precision tiers.  1: FP32 (ftz).  2: FP64 redo of the pairs whose FP32 sum is below kMinAccepted
+// (intel_pairhmm.hpp:137).  3: the reference's FP64 pass also runs flush-to-zero, so products that would
+// be denormal vanish there, while the device keeps them.  That can only show at the 1e-9 level when the
+// final FP64 sum is itself within ~15 orders of magnitude of DBL_MIN (at most 8*R*H flushed products of
+// < 2.2e-308 each, carried forward with weight <= 1): such pairs (log10 likelihood below about -590) are
+// redone by the EXACT FP64 kernel, whose products are flushed by hand.  The FP64 kernel marks them by
+// setting the sign bit of their raw FP32 sum and the (job, chunk) flag to 2.
+constexpr double kFlushDanger = 1e-285;
 // Lane l+1 runs kSkew columns behind lane l.  With 2, the bottom row a lane shuffles down at the end
 // of a step is not consumed until a whole step later (shuffle latency off the X-chain critical path).
 // Measured on the final kernel: no gain (the other warps hide that latency) while the straddling
@@ -108,6 +116,8 @@ struct KernelArgs {
     uint8_t*   job_flags;                // [n_jobs_total * hap_chunks]: 1 = some pair of this (job, chunk)
                                          // underflowed in FP32, so the FP64 kernel has work there
     int32_t    job_flag_base;            // index of this launch's first job in job_flags
+    int32_t    tier;                     // FP64 launches: 2 = redo of FP32 underflows, 3 = flush-exact redo of the
+                                         // pairs whose FP64 sum came out within reach of the denormal range
 };
 
 // ---- precision policies --------------------------------------------------------------------
@@ -128,6 +138,7 @@ struct PolicyF32x2 {
     __device__ static __forceinline__ V mul(V a, V b) {
         unsigned long long r; asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(u64(a)), "l"(u64(b))); return f2(r);
     }
+    __device__ static __forceinline__ V mulx(V a, V b) { return mul(a, b); }   // EXACT product: ftz is in the instruction
     __device__ static __forceinline__ V add(V a, V b) {
         unsigned long long r; asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(u64(a)), "l"(u64(b))); return f2(r);
     }
@@ -169,6 +180,13 @@ struct PolicyF64 {
     __device__ static __forceinline__ S get(const V& v, int) { return v; }
     __device__ static __forceinline__ void set(V& v, int, S s) { v = s; }
     __device__ static __forceinline__ V mul(V a, V b) { return __dmul_rn(a, b); }
+    // EXACT product: the reference runs with MXCSR flush-to-zero (intel_pairhmm.hpp:102-105), which also
+    // flushes DOUBLE denormal results; only products can come out denormal here (every value is >= 0,
+    // so a sum is at least its larger term), and the device has no ftz for FP64, so flush by hand.
+    __device__ static __forceinline__ V mulx(V a, V b) {
+        const double r = __dmul_rn(a, b);
+        return (__double2hiint(r) < 0x00100000) ? 0.0 : r;
+    }
     __device__ static __forceinline__ V add(V a, V b) { return __dadd_rn(a, b); }
     __device__ static __forceinline__ V fma(V a, V b, V c) { return __fma_rn(a, b, c); }
     __device__ static __forceinline__ V addx(V a, V b) { return __dadd_rn(a, b); }
@@ -264,7 +282,11 @@ forward_kernel(const KernelArgs args)
     if (job_idx >= args.n_jobs) return;
 
     uint8_t* const my_flag = args.job_flags + ((size_t)(args.job_flag_base + job_idx) * gridDim.y + blockIdx.y);
-    if (!P::kIsF32 && *my_flag == 0) return;               // nothing to redo here: one byte read, done
+    if (!P::kIsF32 && *my_flag != (args.tier == 3 ? 2 : 1)) return;   // nothing to redo here: one byte read, done
+    // FP64: which pairs this launch redoes, told from their raw FP32 sum
+    auto needs_redo = [&](const float raw) {
+        return args.tier == 3 ? (__float_as_uint(raw) >> 31) != 0u : raw < kMinAccepted;
+    };
     const WarpJob job = args.jobs[job_idx];
     const int hap_beg = args.region_hap_beg[job.region];
     const int nh      = args.region_hap_beg[job.region + 1] - hap_beg;
@@ -301,7 +323,7 @@ forward_kernel(const KernelArgs args)
             bool need = false;
             if (valid[0])
                 for (int h = h_first + l; h < h_last; h += G)
-                    need |= args.raw32[out_base + (int64_t)(rd[0] - rd_beg) * nh + h] < kMinAccepted;
+                    need |= needs_redo(args.raw32[out_base + (int64_t)(rd[0] - rd_beg) * nh + h]);
             if (!__any_sync(0xffffffffu, need)) continue;
         }
         const bool group_live = valid[0];
@@ -392,7 +414,7 @@ forward_kernel(const KernelArgs args)
 #pragma unroll 1
         for (int h = h_first; h < h_last; ++h) {
             if (!P::kIsF32) {
-                const bool w = group_live && (args.raw32[out_base + (int64_t)(rd[0] - rd_beg) * nh + h] < kMinAccepted);
+                const bool w = group_live && needs_redo(args.raw32[out_base + (int64_t)(rd[0] - rd_beg) * nh + h]);
                 if (!__any_sync(0xffffffffu, w)) continue;     // nobody in this warp redoes this haplotype
             }
             const int ho = args.hap_off[hap_beg + h];
@@ -439,6 +461,8 @@ forward_kernel(const KernelArgs args)
         V qM = inM, qX = inX, qY = inY;   // kSkew == 2: bottom row in flight (sent last step, used next step)
 
         const uint32_t tab_addr = (uint32_t)__cvta_generic_to_shared(my_tab);
+        // products: EXACT ones honour the reference's flush-to-zero in both precisions (P::mulx)
+        auto MUL = [](const V a, const V b) { return EXACT ? P::mulx(a, b) : P::mul(a, b); };
         // K cell updates of this lane's current column; `cb` is the column's stream byte
         auto cells = [&](const uint32_t cb) {
             // priors of this column: K entries of the sub-table the haplotype base names.  Issued
@@ -458,24 +482,24 @@ forward_kernel(const KernelArgs args)
                 const V dY = k ? Y[k - 1] : dgY;
                 if (EXACT) {
                     // reference operation order, unfused (avx-pairhmm-template.h:188)
-                    t0[k] = P::addx(P::addx(P::mul(dM, pMM[kk]), P::mul(dX, pGAPM[kk])), P::mul(dY, pGAPM[kk]));
+                    t0[k] = P::addx(P::addx(MUL(dM, pMM[kk]), MUL(dX, pGAPM[kk])), MUL(dY, pGAPM[kk]));
                 } else {
-                    t0[k] = P::fma(dY, pGAPM[kk], P::fma(dX, pGAPM[kk], P::mul(dM, pMM[kk])));
+                    t0[k] = P::fma(dY, pGAPM[kk], P::fma(dX, pGAPM[kk], MUL(dM, pMM[kk])));
                 }
             }
             // Y from the left neighbour (:197); needs M of the previous column
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const int kk = CONSTG ? 0 : k;
-                const V yv = SHARED ? Pm[k] : P::mul(M[k], pMY[kk]);
+                const V yv = SHARED ? Pm[k] : MUL(M[k], pMY[kk]);
                 const V cYY = ALIGNED ? pXXc : pYY[ALIGNED ? 0 : k];
-                Y[k] = EXACT ? P::addx(yv, P::mul(Y[k], cYY)) : P::fma(Y[k], cYY, yv);
+                Y[k] = EXACT ? P::addx(yv, MUL(Y[k], cYY)) : P::fma(Y[k], cYY, yv);
             }
             // Phase B: M = t0 * prior (:152-158, :188)
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                M[k] = P::mul(t0[k], prior[k]);
-                if (SHARED) Pm[k] = P::mul(M[k], pMX[0]);
+                M[k] = MUL(t0[k], prior[k]);
+                if (SHARED) Pm[k] = MUL(M[k], pMX[0]);
             }
             // Phase C: X runs down the column (cell above, :194)
 #pragma unroll
@@ -484,9 +508,9 @@ forward_kernel(const KernelArgs args)
                 const V cXX = (k == 0) ? pXX0 : (CONSTG ? pXXc : pYY[ALIGNED ? 0 : k]);
                 const V uX = k ? X[k - 1] : inX;            // (row-1, c)
                 V um;                                       // M(row-1, c) * pMX(row)
-                if (k == 0) um = P::mul(inM, pMX0);
-                else um = SHARED ? Pm[k - 1] : P::mul(M[k - 1], pMX[kk]);
-                X[k] = EXACT ? P::addx(um, P::mul(uX, cXX)) : P::fma(uX, cXX, um);
+                if (k == 0) um = MUL(inM, pMX0);
+                else um = SHARED ? Pm[k - 1] : MUL(M[k - 1], pMX[kk]);
+                X[k] = EXACT ? P::addx(um, MUL(uX, cXX)) : P::fma(uX, cXX, um);
             }
             // last row of the last lane is the last read row: running sums (:328-343)
             sumM = EXACT ? P::addx(sumM, M[K - 1]) : P::add(sumM, M[K - 1]);
@@ -516,12 +540,16 @@ forward_kernel(const KernelArgs args)
                 for (int hf = 0; hf < NH; ++hf) {
                     const int64_t oi = out_base + (int64_t)(rd[hf] - rd_beg) * nh + h;
                     bool w = valid[hf] && group_live;
-                    if (!P::kIsF32) w = w && (args.raw32[oi] < kMinAccepted);
+                    if (!P::kIsF32) w = w && needs_redo(args.raw32[oi]);
                     if (!w) continue;
                     const S res = P::sadd(P::get(sumM, hf), P::get(sumX, hf));
                     if (P::kIsF32) {
                         args.raw32[oi] = (float)res;
                         if ((float)res < kMinAccepted) *my_flag = 1;
+                    } else if (!EXACT && (double)res < kFlushDanger) {
+                        // tier 3 will redo this pair with flushed products
+                        args.raw32[oi] = __uint_as_float(__float_as_uint(args.raw32[oi]) | 0x80000000u);
+                        *my_flag = 2;
                     } else {
                         const unsigned slot = atomicAdd(args.rescue_count, 1u);
                         args.rescue_out[slot].out_idx = oi;

@@ -81,9 +81,43 @@ def test_random_ragged_batches(pkg, engine, exact_engine, oracle, seed, kw):
     check(exact_engine.compute(b), want, exact=True, what=f"seed {seed} exact")
 
 
+@pytest.mark.parametrize("general,with_n", [(False, False), (False, True), (True, True)])
+def test_every_read_length_1_to_255(pkg, engine, exact_engine, oracle, general, with_n):
+    """One read of every length 1..255: every compiled lane-group shape with every number of dummy rows,
+    lane-aligned and not, odd read counts per shape (idle lane groups, unpaired reads), haplotypes with and
+    without N, and haplotypes shorter than the lane group (several in flight at once).  The long reads
+    against the short haplotypes end near the bottom of the FP64 range, where the reference's
+    flush-to-zero of DOUBLE denormals shows (precision tier 3 of phmm_kernels.cuh)."""
+    rng = np.random.default_rng(77 + general + 2 * with_n)
+    alpha = np.frombuffer(b"ACGT", np.uint8)
+    regions = []
+    for reg in range(2):
+        haps = [alpha[rng.integers(0, 4, int(n))] for n in (311, 97, 5)]
+        if with_n:
+            haps[1] = haps[1].copy(); haps[1][::17] = ord("N")
+        lens = np.arange(1 + reg, 256, 2)                  # odd lengths in region 0, even in region 1
+        rng.shuffle(lens)
+        reads, quals, gi, gd, gc = [], [], [], [], []
+        for rl in lens:
+            rl = int(rl)
+            h = haps[0]
+            o = int(rng.integers(0, len(h) - rl + 1)); r = h[o:o + rl].copy()
+            m = rng.random(rl) < 0.03; r[m] = alpha[rng.integers(0, 4, int(m.sum()))]
+            reads.append(r)
+            quals.append((33 + rng.integers(2, 42, rl)).astype(np.uint8))
+            gi.append((33 + rng.integers(20, 50, rl)).astype(np.uint8))
+            gd.append((33 + rng.integers(20, 50, rl)).astype(np.uint8))
+            gc.append((33 + rng.integers(5, 25, rl)).astype(np.uint8))
+        regions.append((reads, quals, haps, gi, gd, gc) if general else (reads, quals, haps))
+    b = pkg.Batch.from_regions(regions)
+    want = oracle.batch(b, threads=16)
+    check(engine.compute(b), want, what="all lengths fast")
+    check(exact_engine.compute(b), want, exact=True, what="all lengths exact")
+
+
 def test_constant_but_unequal_gap_penalties(pkg, engine, exact_engine, oracle):
     """Batch-constant (i,d,c) with i != d takes kernel MODE 1; NULL arrays and explicit constant arrays agree."""
-    b = pkg.synth.random_small(31, n_regions=4, general_gaps=False)
+    b = pkg.synth.random_small(31, n_regions=4, general_gaps=False, max_read_len=255, max_hap_len=300)
     kw = dict(gap_open_i=ord("I"), gap_open_d=ord("F"), gap_cont_c=ord("-"))
     b1 = pkg.Batch(b.region_read_beg, b.region_hap_beg, b.read_off, b.read_bases, b.read_q, b.hap_off, b.hap_bases, **kw)
     n = len(b.read_bases)
