@@ -24,6 +24,8 @@
 #pragma once
 
 #include <cstdint>
+#include <deque>
+#include <memory>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -48,7 +50,7 @@ public:
             opt.struct_size = (int32_t)sizeof(opt);
             opt.n_devices = devices.empty() ? 1 : (int32_t)devices.size();
             opt.devices = devices.empty() ? nullptr : devices.data();
-            opt.pipeline_depth = 2;
+            opt.pipeline_depth = 4;            // B200RegionBatcher keeps up to 3 batches in flight
             opt.host_threads = 1;
             int rc = phmm_create(&opt, &eng);
             if (rc != PHMM_OK) throw std::runtime_error(std::string("phmm_create: ") + phmm_strerror(rc));
@@ -135,6 +137,173 @@ struct B200PairHMM
     }
 
     phmm_stats last_stats{};
+};
+
+// B200RegionBatcher -- cross-window batching for the caller side of the path.
+//
+// The reference's window loop (haplotypecaller.hpp:138-152) scores one small region at a time; on a
+// B200 a region is well under a millisecond of device time, so one synchronous call per window is all
+// launch and copy latency.  The batcher lets the caller hand over regions as the assembler produces
+// them and collect the matrices later:
+//
+//   hc::B200RegionBatcher batcher;
+//   for (window w) { ...filter, clip, assemble...;  ids[w] = batcher.add_region(haplotypes[w], reads[w]); }
+//   for (window w) { auto likelihoods = batcher.take(ids[w], reads[w]);  genotyper...(reads[w], ..., likelihoods, ...); }
+//
+// add_region() copies the bytes the engine needs into the batch under construction and, once that
+// holds `flush_cells` DP cells (or `flush_regions` regions), submits it asynchronously (phmm_submit);
+// up to `max_in_flight` batches overlap upload, kernels and download while the caller keeps
+// assembling.  take() returns exactly what B200PairHMM::compute_likelihoods would have returned for
+// that region -- capped rows, poorly modelled reads erased from the caller's vector
+// (intel_pairhmm.hpp:24-46) -- so the genotyper consumes it unchanged.  Regions may be taken in any
+// order, each once.  One thread calls add_region()/take() (the engine has one submitter).
+class B200RegionBatcher
+{
+public:
+    explicit B200RegionBatcher(int64_t flush_cells = (int64_t)2e9, int32_t flush_regions = 4096, int max_in_flight = 3)
+        : flush_cells_(flush_cells), flush_regions_(flush_regions), max_in_flight_(max_in_flight), eng_(B200Engine::get()) {}
+    ~B200RegionBatcher() { try { drain(); } catch (...) {} }
+    B200RegionBatcher(const B200RegionBatcher&) = delete;
+    B200RegionBatcher& operator=(const B200RegionBatcher&) = delete;
+
+    template <class HaplotypeT, class ReadT>
+    int add_region(const std::vector<HaplotypeT>& haps, const std::vector<ReadT>& reads)
+    {
+        if (!cur_) cur_ = std::make_unique<Pending>();
+        Pending& b = *cur_;
+        if (b.region_read_beg.empty()) { b.region_read_beg.push_back(0); b.region_hap_beg.push_back(0); b.read_off.push_back(0); b.hap_off.push_back(0); b.out_beg.push_back(0); }
+        int64_t read_bytes = 0, hap_bytes = 0;
+        for (const auto& r : reads) {
+            if (r.SEQ.size() != r.QUAL.size()) throw std::runtime_error("B200RegionBatcher: SEQ and QUAL lengths differ");
+            b.read_bases.insert(b.read_bases.end(), r.SEQ.begin(), r.SEQ.end());
+            b.read_q.insert(b.read_q.end(), r.QUAL.begin(), r.QUAL.end());
+            b.read_off.push_back((int32_t)b.read_bases.size());
+            read_bytes += (int64_t)r.SEQ.size();
+        }
+        for (const auto& h : haps) {
+            b.hap_bases.insert(b.hap_bases.end(), h.bases.begin(), h.bases.end());
+            b.hap_off.push_back((int32_t)b.hap_bases.size());
+            hap_bytes += (int64_t)h.bases.size();
+        }
+        b.region_read_beg.push_back((int32_t)(b.read_off.size() - 1));
+        b.region_hap_beg.push_back((int32_t)(b.hap_off.size() - 1));
+        b.out_beg.push_back(b.out_beg.back() + (int64_t)reads.size() * (int64_t)haps.size());
+        b.cells += read_bytes * hap_bytes;
+        const int id = (int)where_.size();
+        where_.push_back({next_batch_id_, (int32_t)(b.region_read_beg.size() - 2)});
+        if (b.cells >= flush_cells_ || (int32_t)(b.region_read_beg.size() - 1) >= flush_regions_) flush();
+        return id;
+    }
+
+    // submit the batch under construction now (called automatically by add_region / take / drain)
+    void flush()
+    {
+        if (!cur_ || cur_->region_read_beg.size() <= 1) return;
+        while ((int)in_flight_ >= max_in_flight_) wait_oldest();
+        Pending& b = *cur_;
+        phmm_batch pb{};
+        pb.n_regions = (int32_t)(b.region_read_beg.size() - 1);
+        pb.n_reads = (int32_t)(b.read_off.size() - 1);
+        pb.n_haps = (int32_t)(b.hap_off.size() - 1);
+        pb.region_read_beg = b.region_read_beg.data();
+        pb.region_hap_beg = b.region_hap_beg.data();
+        pb.read_off = b.read_off.data();
+        pb.read_bases = b.read_bases.data();
+        pb.read_q = b.read_q.data();
+        pb.read_i = pb.read_d = pb.read_c = nullptr;                   // constant strings of sam/sam.hpp:30-32
+        pb.gap_open_i = (uint8_t)B200PairHMM::GAP_OPEN; pb.gap_open_d = (uint8_t)B200PairHMM::GAP_OPEN;
+        pb.gap_cont_c = (uint8_t)B200PairHMM::GAP_CONT;
+        pb.hap_off = b.hap_off.data();
+        pb.hap_bases = b.hap_bases.data();
+        b.lik.resize((size_t)b.out_beg.back());
+        int rc = phmm_submit(eng_, &pb, &b.ticket);
+        if (rc != PHMM_OK) throw std::runtime_error(std::string("phmm_submit: ") + phmm_strerror(rc) + ": " + phmm_last_error(eng_));
+        // inputs were copied to pinned staging; keep only what take() needs
+        b.read_bases.clear(); b.read_bases.shrink_to_fit(); b.read_q.clear(); b.read_q.shrink_to_fit();
+        b.hap_bases.clear(); b.hap_bases.shrink_to_fit();
+        b.submitted = true;
+        ++in_flight_; ++batches_submitted;
+        batches_.push_back(std::move(cur_));
+        ++next_batch_id_;
+    }
+
+    template <class ReadT>
+    std::vector<std::vector<double>> take(int region_id, std::vector<ReadT>& reads)
+    {
+        if (region_id < 0 || region_id >= (int)where_.size()) throw std::runtime_error("B200RegionBatcher: unknown region id");
+        const Where w = where_[region_id];
+        if (w.batch == next_batch_id_) flush();                          // still under construction
+        Pending& b = *batches_.at((size_t)(w.batch - first_batch_id_));
+        while (!b.done) wait_oldest();
+        const int32_t r0 = b.region_read_beg[w.region], r1 = b.region_read_beg[w.region + 1];
+        const int32_t h0 = b.region_hap_beg[w.region], h1 = b.region_hap_beg[w.region + 1];
+        const std::size_t n_reads = (std::size_t)(r1 - r0), n_haps = (std::size_t)(h1 - h0);
+        if (n_reads != reads.size()) throw std::runtime_error("B200RegionBatcher: reads vector differs from the one added");
+        std::vector<std::vector<double>> out(n_reads, std::vector<double>(n_haps));
+        if (n_reads == 0 || n_haps == 0) return out;
+        double* flat = b.lik.data() + b.out_beg[w.region];
+        std::vector<int32_t> read_len(n_reads);
+        for (std::size_t r = 0; r < n_reads; r++) read_len[r] = b.read_off[r0 + r + 1] - b.read_off[r0 + r];
+        std::vector<uint8_t> keep(n_reads);
+        phmm_normalize_filter(flat, (int32_t)n_reads, (int32_t)n_haps, read_len.data(), keep.data());   // :24-46
+        std::size_t k = 0;
+        for (std::size_t r = 0; r < n_reads; r++) {
+            if (!keep[r]) continue;
+            out[k].assign(flat + r * n_haps, flat + (r + 1) * n_haps);
+            if (k != r) reads[k] = std::move(reads[r]);
+            ++k;
+        }
+        out.resize(k);
+        reads.erase(reads.begin() + k, reads.end());
+        return out;
+    }
+
+    // wait for everything submitted so far
+    void drain() { flush(); while (in_flight_) wait_oldest(); }
+
+    int batches_submitted = 0;
+    phmm_stats total_stats{};          // summed over finished batches (kernel_ms: sum, not max)
+
+private:
+    struct Pending {
+        std::vector<int32_t> region_read_beg, region_hap_beg, read_off, hap_off;
+        std::vector<int64_t> out_beg;
+        std::vector<uint8_t> read_bases, read_q, hap_bases;
+        std::vector<double> lik;
+        int64_t cells = 0;
+        phmm_ticket ticket = 0;
+        bool submitted = false, done = false;
+    };
+    struct Where { int batch; int32_t region; };
+
+    void wait_oldest()
+    {
+        for (auto& pb : batches_) {
+            Pending& b = *pb;
+            if (!b.submitted || b.done) continue;
+            phmm_result res{};
+            res.log10_lik = b.lik.data();
+            int rc = phmm_wait(eng_, b.ticket, &res);
+            if (rc != PHMM_OK) throw std::runtime_error(std::string("phmm_wait: ") + phmm_strerror(rc) + ": " + phmm_last_error(eng_));
+            b.done = true; --in_flight_;
+            total_stats.n_pairs += res.stats.n_pairs; total_stats.n_cells += res.stats.n_cells;
+            total_stats.n_rescued += res.stats.n_rescued; total_stats.h2d_bytes += res.stats.h2d_bytes;
+            total_stats.d2h_bytes += res.stats.d2h_bytes; total_stats.kernel_launches += res.stats.kernel_launches;
+            total_stats.kernel_ms += res.stats.kernel_ms;
+            return;
+        }
+        throw std::runtime_error("B200RegionBatcher: nothing in flight");
+    }
+
+    int64_t flush_cells_;
+    int32_t flush_regions_;
+    int max_in_flight_;
+    phmm_engine* eng_;
+    std::unique_ptr<Pending> cur_;
+    std::deque<std::unique_ptr<Pending>> batches_;
+    std::vector<Where> where_;
+    int next_batch_id_ = 0, first_batch_id_ = 0;
+    int in_flight_ = 0;
 };
 
 } // namespace hc

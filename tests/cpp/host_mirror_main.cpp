@@ -2,6 +2,9 @@
 // that carry the members the engine touches.  Prints the kept read indices and the matrix (%.17g) so
 // tests/test_cpp_mirror.py can compare it with the Python face and the golden fixtures.
 //   usage: host_mirror_main <region.txt>     lines: "H <bases>" | "R <seq> <qual>"
+//          host_mirror_main --batched <r1.txt> <r2.txt> ...   every region through hc::B200RegionBatcher (tiny
+//          flush threshold, so several asynchronous batches), taken in REVERSE order; prints "region <i>"
+//          before each region's block
 #include <cstdio>
 #include <fstream>
 #include <iostream>
@@ -14,24 +17,54 @@
 struct Haplotype { std::string bases; };
 struct SAMRecord { std::string QNAME, SEQ, QUAL; std::size_t size() const { return SEQ.size(); } };
 
-int main(int argc, char** argv)
+static void load(const char* path, std::vector<Haplotype>& haps, std::vector<SAMRecord>& reads)
 {
-    if (argc < 2) { std::fprintf(stderr, "usage: %s region.txt\n", argv[0]); return 2; }
-    std::ifstream in(argv[1]);
-    std::vector<Haplotype> haps; std::vector<SAMRecord> reads;
+    std::ifstream in(path);
     std::string line;
     while (std::getline(in, line)) {
         std::istringstream is(line); std::string tag; is >> tag;
         if (tag == "H") { Haplotype h; is >> h.bases; haps.push_back(h); }
         else if (tag == "R") { SAMRecord r; is >> r.SEQ >> r.QUAL; r.QNAME = std::to_string(reads.size()); reads.push_back(r); }
     }
+}
+
+static void print(const std::vector<SAMRecord>& reads, const std::vector<std::vector<double>>& lik)
+{
+    std::printf("kept");
+    for (auto& r : reads) std::printf(" %s", r.QNAME.c_str());
+    std::printf("\n");
+    for (auto& row : lik) { for (double v : row) std::printf("%.17g ", v); std::printf("\n"); }
+}
+
+int main(int argc, char** argv)
+{
+    if (argc < 2) { std::fprintf(stderr, "usage: %s [--batched] region.txt ...\n", argv[0]); return 2; }
+    if (std::string(argv[1]) == "--batched") {
+        const int n = argc - 2;
+        std::vector<std::vector<Haplotype>> haps(n);
+        std::vector<std::vector<SAMRecord>> reads(n);
+        std::vector<int> ids(n);
+        try {
+            hc::B200RegionBatcher batcher(/*flush_cells=*/20000, /*flush_regions=*/3, /*max_in_flight=*/2);
+            for (int i = 0; i < n; i++) { load(argv[2 + i], haps[i], reads[i]); ids[i] = batcher.add_region(haps[i], reads[i]); }
+            for (int i = n - 1; i >= 0; i--) {
+                auto lik = batcher.take(ids[i], reads[i]);
+                std::printf("region %d\n", i);
+                print(reads[i], lik);
+            }
+            std::fprintf(stderr, "batches %d\n", batcher.batches_submitted);
+        } catch (const std::exception& e) {
+            std::fprintf(stderr, "error: %s\n", e.what());
+            return 1;
+        }
+        return 0;
+    }
+    std::vector<Haplotype> haps; std::vector<SAMRecord> reads;
+    load(argv[1], haps, reads);
     try {
         hc::B200PairHMM pairhmm;                                  // haplotypecaller.hpp:90
         auto lik = pairhmm.compute_likelihoods(haps, reads);      // :103
-        std::printf("kept");
-        for (auto& r : reads) std::printf(" %s", r.QNAME.c_str());
-        std::printf("\n");
-        for (auto& row : lik) { for (double v : row) std::printf("%.17g ", v); std::printf("\n"); }
+        print(reads, lik);
     } catch (const std::exception& e) {
         std::fprintf(stderr, "error: %s\n", e.what());
         return 1;

@@ -53,3 +53,35 @@ def test_cpp_mirror_matches_reference_call_surface(exe, tmp_path, golden):
         got = np.array([[float(x) for x in ln.split()] for ln in lines[1:]]).reshape(len(kept), -1)
         want = np.array(reg["lik_bits"], np.uint64).view(np.float64).reshape(got.shape)
         assert np.abs(got - want).max() <= 1e-4
+
+
+@pytest.mark.gpu
+def test_region_batcher_equals_per_region_calls(exe, tmp_path, golden):
+    """hc::B200RegionBatcher (cross-window batching, SURVEY 8f-2): regions added one by one, flushed into
+    several asynchronous batches, taken in reverse order -> the same kept reads and the same matrix
+    (to the bit) as one hc::B200PairHMM::compute_likelihoods call per region."""
+    a2 = golden["kat_appendix_a"]["a2"]
+    regions = [a2] + golden["ref_region_filter"]["regions"]
+    regions = regions + regions[::-1]
+    paths = []
+    for i, reg in enumerate(regions):
+        p = tmp_path / f"b{i}.txt"
+        _region_file(p, reg)
+        paths.append(str(p))
+    single = []
+    for p in paths:
+        r = subprocess.run([exe, p], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        single.append([ln.rstrip() for ln in r.stdout.strip().splitlines()])
+    r = subprocess.run([exe, "--batched"] + paths, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert int(r.stderr.strip().split()[-1]) >= 2                       # really several batches
+    blocks, cur = {}, None
+    for ln in r.stdout.strip().splitlines():
+        if ln.startswith("region "):
+            cur = int(ln.split()[1]); blocks[cur] = []
+        else:
+            blocks[cur].append(ln.rstrip())
+    assert sorted(blocks) == list(range(len(paths)))
+    for i in range(len(paths)):
+        assert blocks[i] == single[i], f"region {i}"

@@ -16,14 +16,15 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_EXE = os.path.join(ROOT, "oracle", "_ref", "hc_e2e_ref")
 B200_EXE = os.path.join(ROOT, "oracle", "_ref", "hc_e2e_b200")
+BATCHED_EXE = os.path.join(ROOT, "oracle", "_ref", "hc_e2e_b200_batched")
 GOLDEN = os.path.join(ROOT, "tests", "golden", "chrm_like.ref.vcf")
 needs = pytest.mark.skipif(not (os.path.exists(REF_EXE) and os.path.exists(B200_EXE)),
                            reason="oracle/_ref/hc_e2e_* not built (needs /root/reference at build time)")
 
 
-def _run(exe, prefix, out):
+def _run(exe, prefix, out, extra=()):
     t0 = time.perf_counter()
-    r = subprocess.run([exe, "-I", prefix + ".sam", "-R", prefix + ".fa", "-O", out], capture_output=True, text=True)
+    r = subprocess.run([exe, "-I", prefix + ".sam", "-R", prefix + ".fa", "-O", out, *extra], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
     return time.perf_counter() - t0, r.stderr.strip().splitlines()[-1]
 
@@ -57,3 +58,16 @@ def test_b200_engine_end_to_end_vcf_is_bit_identical(data, tmp_path):
     print(f"\nchrM-like e2e wall: reference engine {t_ref:.2f} s ({log_ref}) | B200 engine {t_b200:.2f} s ({log_b200})")
     assert open(b200_out, "rb").read() == open(ref_out, "rb").read()
     assert open(b200_out).read() == open(GOLDEN).read()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(BATCHED_EXE), reason="oracle/_ref/hc_e2e_b200_batched not built")
+@pytest.mark.parametrize("threads", [1, 8])
+def test_batched_driver_vcf_is_bit_identical(data, tmp_path, threads):
+    """windows assembled on `threads` host threads, all regions of the contig scored in a few
+    asynchronous cross-window batches (hc::B200RegionBatcher), genotyped in window order."""
+    prefix, _ = data
+    out = str(tmp_path / "batched.vcf")
+    t, log = _run(BATCHED_EXE, prefix, out, extra=("-T", str(threads)))
+    print(f"\nchrM-like e2e wall, batched driver, {threads} assembly thread(s): {t:.2f} s ({log})")
+    assert open(out).read() == open(GOLDEN).read()
