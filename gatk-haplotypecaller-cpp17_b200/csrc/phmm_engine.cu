@@ -132,6 +132,7 @@ struct Part {
     int mode = kModeGeneral;                 // kernel MODE: general / batch-constant gaps / constant with i == d
     uint8_t gap[3] = {0, 0, 0};              // the batch-constant (i, d, c) bytes when mode != general
     int max_H = 0, max_nh = 0;
+    int n_long = 0;                          // (long read, haplotype) pairs of the one-warp-per-pair kernel
     int n_jobs = 0;
     int job_beg[2 * kNumShapes + 1] = {0};  // jobs are grouped by kernel slot = shape + kNumShapes * aligned
     int haps_per_job = 1, hap_chunks = 1;
@@ -153,6 +154,7 @@ struct Slot {
     bool busy = false;
     Part part;
     KernelArgs args{};
+    const LongPair* d_long = nullptr;
 };
 
 struct phmm_engine_impl;
@@ -261,7 +263,7 @@ int validate_batch(const phmm_batch* b, std::string& err)
     for (int r = 0; r < b->n_reads; r++) {
         int R = b->read_off[r + 1] - b->read_off[r];
         if (R < 1) { err = "empty read"; return PHMM_ERR_INVALID_ARG; }
-        if (R > kMaxReadLenCompiled) { err = "read longer than " + std::to_string(kMaxReadLenCompiled); return PHMM_ERR_UNSUPPORTED; }
+        if (R > kLongMaxRead) { err = "read longer than " + std::to_string(kLongMaxRead); return PHMM_ERR_UNSUPPORTED; }
     }
     for (int h = 0; h < b->n_haps; h++) {
         int H = b->hap_off[h + 1] - b->hap_off[h];
@@ -289,14 +291,19 @@ int64_t region_cells(const phmm_batch* b, int g)
 // Forward (FP32) and rescue (FP64) kernels of a staged slot.  Every kernel slot (shape x aligned) is an
 // independent launch pair; they are spread over a few auxiliary streams forked from / joined to the
 // slot's stream so that the small grids of a ragged batch overlap.  ev_k0 / ev_k1 bracket the lot.
-int launch_kernels(Slot& s, bool exact, bool skip_rescue, std::string& err)
+// Precision tiers [tier_lo, tier_hi] (phmm_kernels.cuh): 1 FP32, 2 its FP64 redo, 3 the flush-exact FP64
+// redo of pairs that ended within reach of the denormal range.  The normal pass is tiers 1-2; tier 3 is
+// launched by finalize_part only when the downloaded results show a marked pair (pathological inputs).
+int launch_kernels(Slot& s, bool exact, int tier_lo, int tier_hi, std::string& err)
 {
     Part& p = s.part;
     const KernelArgs& a = s.args;
-    p.launches = 0;
-    CUDA_TRY(cudaMemsetAsync(s.d_out.p, 0, 16, s.stream));
-    CUDA_TRY(cudaMemsetAsync(s.d_flags.p, 0, (size_t)p.n_jobs * p.hap_chunks, s.stream));
-    CUDA_TRY(cudaEventRecord(s.ev_k0, s.stream));
+    if (tier_lo == 1) {
+        p.launches = 0;
+        CUDA_TRY(cudaMemsetAsync(s.d_out.p, 0, 16, s.stream));
+        CUDA_TRY(cudaMemsetAsync(s.d_flags.p, 0, (size_t)p.n_jobs * p.hap_chunks, s.stream));
+        CUDA_TRY(cudaEventRecord(s.ev_k0, s.stream));
+    }
     int n_kernels = 0;
     for (int k = 0; k < 2 * kNumShapes; k++) n_kernels += (p.job_beg[k + 1] > p.job_beg[k]);
     const bool fork = n_kernels > 1;
@@ -320,11 +327,7 @@ int launch_kernels(Slot& s, bool exact, bool skip_rescue, std::string& err)
         ak.job_flag_base = p.job_beg[k];
         ak.smem_bytes_per_warp = per_warp;
         dim3 grid((n + kWarpsPerCta - 1) / kWarpsPerCta, p.hap_chunks);
-        // tier 1 FP32, tier 2 its FP64 redo, tier 3 (fast engine only) the flush-exact FP64 redo of pairs that
-        // ended within reach of the denormal range -- the EXACT FP64 kernel; it finds no flagged work and
-        // exits at once in all but pathological batches
-        const int n_tiers = skip_rescue ? 1 : (exact ? 2 : 3);
-        for (int tier = 1; tier <= n_tiers; tier++) {
+        for (int tier = tier_lo; tier <= tier_hi; tier++) {       // tier 3 runs the EXACT FP64 kernel
             KernelFn fn = kernel_table().fn[tier >= 2][(exact || tier == 3) ? 1 : 0][p.mode][k / kNumShapes][k % kNumShapes];
             ak.tier = tier;
             if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -339,7 +342,14 @@ int launch_kernels(Slot& s, bool exact, bool skip_rescue, std::string& err)
                 CUDA_TRY(cudaEventRecord(s.ev_join[ai], s.aux[ai]));
                 CUDA_TRY(cudaStreamWaitEvent(s.stream, s.ev_join[ai], 0));
             }
-    CUDA_TRY(cudaEventRecord(s.ev_k1, s.stream));
+    if (tier_lo == 1) {
+        if (p.n_long) {      // reads beyond one lane-group pass: all precision tiers inside one launch
+            launch_long_reads(a, s.d_long, p.n_long, p.mode == kModeGeneral, exact, s.stream);
+            CUDA_TRY(cudaGetLastError());
+            p.launches++;
+        }
+        CUDA_TRY(cudaEventRecord(s.ev_k1, s.stream));
+    }
     return PHMM_OK;
 }
 
@@ -389,6 +399,7 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
             const int h_avg = (int)((b->hap_off[b->region_hap_beg[g + 1]] - b->hap_off[b->region_hap_beg[g]]) / nh);
             for (int r = b->region_read_beg[g]; r < b->region_read_beg[g + 1]; r++) {
                 const int R = b->read_off[r + 1] - b->read_off[r];
+                if (R > kMaxReadLenCompiled) continue;
                 const int sh = pick_shape(R, h_avg);
                 n_all[sh]++; n_al[sh] += is_aligned(R, sh);
             }
@@ -396,7 +407,10 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
         for (int sh = 0; sh < kNumShapes; sh++) use_aligned[sh] = n_al[sh] * 10 >= n_all[sh] * 9;
     }
     std::vector<WarpJob> jobs_k[kSlots];
-    for (int g = g0; g < g1; g++) {
+    std::vector<LongPair> long_pairs;
+    int64_t out_acc = 0;                     // first output index of region g within this part
+    for (int g = g0; g < g1; out_acc += (int64_t)(b->region_read_beg[g + 1] - b->region_read_beg[g]) *
+                                        (b->region_hap_beg[g + 1] - b->region_hap_beg[g]), g++) {
         WarpJob pending[kSlots];
         int n_pending[kSlots];
         for (int k = 0; k < kSlots; k++) n_pending[k] = 0;
@@ -415,6 +429,12 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
         for (int r = b->region_read_beg[g]; r < b->region_read_beg[g + 1]; r++) {
             const int R = b->read_off[r + 1] - b->read_off[r];
             p.n_cells += (int64_t)R * hap_sum;
+            if (R > kMaxReadLenCompiled) {       // beyond one lane-group pass: phmm_long.cu, one warp per pair
+                for (int h = 0; h < nh; h++)
+                    long_pairs.push_back({r - r0, b->region_hap_beg[g] - h0 + h,
+                                          out_acc + (int64_t)(r - b->region_read_beg[g]) * nh + h});
+                continue;
+            }
             const int sh = pick_shape(R, h_avg);
             // lane-aligned reads (length a multiple of K, at least K dummy rows) take the ALIGNED kernels,
             // provided most reads of that shape do (otherwise the split only fragments the launches)
@@ -457,6 +477,8 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
     const size_t o_gc       = general ? take(read_bytes) : 0;
     const size_t o_haps     = take(hap_bytes);
     const size_t o_jobs     = take(sizeof(WarpJob) * p.n_jobs);
+    p.n_long = (int)long_pairs.size();
+    const size_t o_long     = take(sizeof(LongPair) * long_pairs.size());
     const size_t in_bytes   = off;
 
     CUDA_TRY(s.h_in.reserve(in_bytes));
@@ -493,6 +515,7 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
             std::memcpy(hp + o_gc, b->read_c + rb0, read_bytes);
         }
         std::memcpy(hp + o_haps, b->hap_bases + hb0, hap_bytes);
+        if (!long_pairs.empty()) std::memcpy(hp + o_long, long_pairs.data(), sizeof(LongPair) * long_pairs.size());
         WarpJob* jd = (WarpJob*)(hp + o_jobs);
         for (int k = 0; k < kSlots; k++)
             if (!jobs_k[k].empty()) std::memcpy(jd + p.job_beg[k], jobs_k[k].data(), sizeof(WarpJob) * jobs_k[k].size());
@@ -524,6 +547,7 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
     a.hap_bases = dp + o_haps;
     a.ph2pr_f = dc.d_ph2pr_f; a.mm_f = dc.d_mm_f; a.ph2pr_d = dc.d_ph2pr_d; a.mm_d = dc.d_mm_d;
     a.jobs = (const WarpJob*)(dp + o_jobs);
+    s.d_long = (const LongPair*)(dp + o_long);
     a.n_jobs = 0;
     a.haps_per_job = p.haps_per_job;
     a.stream_cap = (int32_t)((2 * (kSkew * 31 + 3) + (size_t)p.haps_per_job * (p.max_H + 1) + 127) / 128 * 128);
@@ -538,7 +562,7 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
     p.h2d_bytes = in_bytes;
     if (!do_launch) return PHMM_OK;
 
-    int rc = launch_kernels(s, exact, false, err);
+    int rc = launch_kernels(s, exact, 1, 2, err);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(s.h_out.p, s.d_out.p, out_bytes, cudaMemcpyDeviceToHost, s.stream));
     CUDA_TRY(cudaEventRecord(s.ev_done, s.stream));
@@ -556,34 +580,27 @@ int finalize_part(phmm_engine* e, DeviceCtx& dc, Slot& s, phmm_result* r, std::s
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1));
     p.kernel_ms = ms;
-    const unsigned count = *(const unsigned*)s.h_out.p;
-    p.rescue_count = count;
+    unsigned count = *(const unsigned*)s.h_out.p;
     const float* raw32 = (const float*)((const uint8_t*)s.h_out.p + 16);
     if (count > (uint64_t)p.n_pairs) { err = "rescue counter overflow"; return PHMM_ERR_CUDA; }
-    if (count) {
-        CUDA_TRY(s.h_rescue.reserve(sizeof(RescueOut) * (size_t)count));
-        CUDA_TRY(cudaMemcpyAsync(s.h_rescue.p, s.d_rescue.p, sizeof(RescueOut) * (size_t)count, cudaMemcpyDeviceToHost, s.stream));
-        CUDA_TRY(cudaStreamSynchronize(s.stream));
-        p.d2h_bytes += sizeof(RescueOut) * (size_t)count;
-    }
     const Tables& T = host_tables();
     double* out = r->log10_lik + p.out0;
     float* o32 = r->raw32 ? r->raw32 + p.out0 : nullptr;
     double* o64 = r->raw64 ? r->raw64 + p.out0 : nullptr;
     uint8_t* ores = r->rescued ? r->rescued + p.out0 : nullptr;
     const float log10_init_f = T.log10_init_f;
-    std::atomic<int64_t> need_rescue{0};
+    std::atomic<int64_t> need_rescue{0}, marked{0};
     auto body = [&](int64_t i0, int64_t i1) {
-        int64_t nr = 0;
+        int64_t nr = 0, nm = 0;
         for (int64_t i = i0; i < i1; i++) {
             const float f = raw32[i];
-            if (f < kMinAccepted) { nr++; out[i] = std::nan(""); }
+            if (f < kMinAccepted) { nr++; nm += std::signbit(f); out[i] = std::nan(""); }
             else out[i] = (double)(log10f(f) - log10_init_f);       // float subtraction, :142
-            if (o32) o32[i] = std::fabs(f);     // the sign bit only marks pairs the flush-exact FP64 tier redid
+            if (o32) o32[i] = std::fabs(f);     // the sign bit only marks pairs for the flush-exact FP64 tier
             if (o64) o64[i] = 0.0;
             if (ores) ores[i] = 0;
         }
-        need_rescue += nr;
+        need_rescue += nr; marked += nm;
     };
     const int nt = (int)std::min<int64_t>(e->host_threads, std::max<int64_t>(1, p.n_pairs / 65536));
     if (nt <= 1) body(0, p.n_pairs);
@@ -592,6 +609,24 @@ int finalize_part(phmm_engine* e, DeviceCtx& dc, Slot& s, phmm_result* r, std::s
         for (int t = 0; t < nt; t++)
             th.emplace_back(body, p.n_pairs * t / nt, p.n_pairs * (t + 1) / nt);
         for (auto& x : th) x.join();
+    }
+    if (marked.load()) {
+        // tier 3: pairs whose FP64 sum came out within reach of the denormal range are redone by the
+        // flush-exact FP64 kernels now; they append to the same rescue list
+        int rc3 = launch_kernels(s, e->opt.exact_fp32 != 0, 3, 3, err);
+        if (rc3) return rc3;
+        CUDA_TRY(cudaMemcpyAsync(s.h_out.p, s.d_out.p, 16, cudaMemcpyDeviceToHost, s.stream));
+        CUDA_TRY(cudaStreamSynchronize(s.stream));
+        count = *(const unsigned*)s.h_out.p;
+        p.d2h_bytes += 16;
+        if (count > (uint64_t)p.n_pairs) { err = "rescue counter overflow"; return PHMM_ERR_CUDA; }
+    }
+    p.rescue_count = count;
+    if (count) {
+        CUDA_TRY(s.h_rescue.reserve(sizeof(RescueOut) * (size_t)count));
+        CUDA_TRY(cudaMemcpyAsync(s.h_rescue.p, s.d_rescue.p, sizeof(RescueOut) * (size_t)count, cudaMemcpyDeviceToHost, s.stream));
+        CUDA_TRY(cudaStreamSynchronize(s.stream));
+        p.d2h_bytes += sizeof(RescueOut) * (size_t)count;
     }
     if ((uint64_t)need_rescue.load() != count) {
         err = "rescue list size " + std::to_string(count) + " != FP32 underflows " + std::to_string(need_rescue.load());
@@ -933,7 +968,7 @@ int phmm_run_staged(phmm_engine* e, phmm_staged* st, int32_t iters, float* ms_pe
             static const bool skip_rescue = getenv("PHMM_EXP_SKIP_RESCUE") != nullptr;   // timing experiments only
             // device time of `iters` back-to-back passes: sum of the per-pass [ev_k0, ev_k1] brackets
             for (int it = 0; it < iters; it++) {
-                int rc2 = launch_kernels(s, exact, skip_rescue, err);
+                int rc2 = launch_kernels(s, exact, 1, skip_rescue ? 1 : 2, err);
                 if (rc2) return rc2;
                 CUDA_TRY(cudaEventSynchronize(s.ev_k1));
                 float one = 0.f;

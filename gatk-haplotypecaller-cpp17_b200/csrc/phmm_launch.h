@@ -18,6 +18,12 @@ constexpr Shape kShapes[kNumShapes] = {
     {16, 1}, {16, 2}, {16, 3}, {16, 4}, {16, 5}, {16, 6}, {16, 7}, {16, 8}, {16, 9}, {16, 10}};
 constexpr int kMaxReadLenCompiled = 32 * 8 - 1;   // 255
 
+// Reads longer than kMaxReadLenCompiled take the one-warp-per-pair kernel of phmm_long.cu.
+constexpr int kLongMaxRead = 2048;           // == PHMM_MAX_READ_LEN (include/phmm.h)
+constexpr int kLongWarpsPerCta = 2;
+struct LongPair { int32_t read, hap; int64_t out_idx; };   // read / haplotype: indices into the part's offset arrays
+void launch_long_reads(const KernelArgs& args, const LongPair* pairs, int n_pairs, bool general, bool exact, cudaStream_t st);
+
 constexpr int kNumModes = 3;
 // tab[mode][aligned][shape]; aligned = every read length of the job is a multiple of K (constant-gap
 // modes only; the general mode has no aligned variant and its [1] row repeats [0])

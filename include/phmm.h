@@ -59,7 +59,8 @@ enum {
     PHMM_ERR_BAD_TICKET  = 6
 };
 
-#define PHMM_MAX_READ_LEN 255     /* rows of one lane-group pass (K*G - 1); longer reads: PHMM_ERR_UNSUPPORTED */
+#define PHMM_MAX_READ_LEN 2048    /* reads of up to 255 bases take the register-tiled kernels, longer ones a
+                                     slower one-warp-per-pair kernel; beyond this: PHMM_ERR_UNSUPPORTED       */
 #define PHMM_MAX_HAP_LEN  8192    /* columns staged in shared memory per lane group            */
 
 typedef struct phmm_engine phmm_engine;

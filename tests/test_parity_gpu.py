@@ -115,6 +115,37 @@ def test_every_read_length_1_to_255(pkg, engine, exact_engine, oracle, general, 
     check(exact_engine.compute(b), want, exact=True, what="all lengths exact")
 
 
+@pytest.mark.parametrize("general", [False, True])
+def test_reads_longer_than_one_lane_group_pass(pkg, engine, exact_engine, oracle, general):
+    """Reads of 256..2048 bases take the one-warp-per-pair kernel (phmm_long.cu); mixed in one region with
+    short reads (register-tiled kernels), against haplotypes longer and shorter than the reads, with N.
+    Good matches stay FP32, poor ones are redone in FP64 inside the same launch."""
+    rng = np.random.default_rng(300 + general)
+    alpha = np.frombuffer(b"ACGT", np.uint8)
+    regions = []
+    for reg in range(2):
+        haps = [alpha[rng.integers(0, 4, int(n))] for n in (2300, 700, 40)]
+        haps[1] = haps[1].copy(); haps[1][::53] = ord("N")
+        haps.append(np.concatenate([haps[0][:1000], haps[0][1003:]]))      # a 3-base deletion of hap 0
+        lens = [256, 257, 300, 511, 512, 513, 777, 1024, 1500, 2047, 2048, 100, 255, 31] if reg == 0 else [256, 1025, 64, 2048]
+        reads, quals, gi, gd, gc = [], [], [], [], []
+        for rl in lens:
+            h = haps[0]
+            o = int(rng.integers(0, len(h) - rl + 1)); r = h[o:o + rl].copy()
+            m = rng.random(rl) < 0.01; r[m] = alpha[rng.integers(0, 4, int(m.sum()))]
+            reads.append(r)
+            quals.append((33 + rng.integers(20, 42, rl)).astype(np.uint8))
+            gi.append((33 + rng.integers(30, 50, rl)).astype(np.uint8))
+            gd.append((33 + rng.integers(30, 50, rl)).astype(np.uint8))
+            gc.append((33 + rng.integers(5, 25, rl)).astype(np.uint8))
+        regions.append((reads, quals, haps, gi, gd, gc) if general else (reads, quals, haps))
+    b = pkg.Batch.from_regions(regions)
+    want = oracle.batch(b, threads=16)
+    assert want["rescued"].any() and not want["rescued"].all()
+    check(engine.compute(b), want, what="long reads fast")
+    check(exact_engine.compute(b), want, exact=True, what="long reads exact")
+
+
 def test_constant_but_unequal_gap_penalties(pkg, engine, exact_engine, oracle):
     """Batch-constant (i,d,c) with i != d takes kernel MODE 1; NULL arrays and explicit constant arrays agree."""
     b = pkg.synth.random_small(31, n_regions=4, general_gaps=False, max_read_len=255, max_hap_len=300)
@@ -234,7 +265,7 @@ def test_edge_cases_and_errors(pkg, engine, oracle):
     check(engine.compute(b), oracle.batch(b), what="R=255 H=3000")
     # errors: read too long -> UNSUPPORTED (5); empty read -> INVALID_ARG (1); bad ticket (6)
     with pytest.raises(pkg.PhmmError) as ei:
-        engine.compute(B.from_regions([([np.full(256, 65, np.uint8)], [np.full(256, 70, np.uint8)], [b"ACGT"])]))
+        engine.compute(B.from_regions([([np.full(2049, 65, np.uint8)], [np.full(2049, 70, np.uint8)], [b"ACGT"])]))
     assert ei.value.code == 5
     with pytest.raises(pkg.PhmmError) as ei:
         engine.compute(B.from_regions([([b""], [b""], [b"ACGT"])]))
