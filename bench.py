@@ -232,6 +232,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from __graft_entry__ import load_package

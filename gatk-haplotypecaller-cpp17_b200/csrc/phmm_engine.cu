@@ -357,6 +357,8 @@ int launch_kernels(Slot& s, bool exact, int tier_lo, int tier_hi, std::string& e
 int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1, int64_t out0,
                      bool exact, bool do_launch, std::string& err)
 {
+    static const bool trace = getenv("PHMM_TRACE") != nullptr;      // development aid: host time per phase
+    const auto t_begin = std::chrono::steady_clock::now();
     Part& p = s.part;
     p = Part();
     p.g0 = g0; p.g1 = g1; p.out0 = out0;
@@ -462,6 +464,7 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
         p.hap_chunks = (nhm + hpj - 1) / hpj;
     }
 
+    const auto t_planned = std::chrono::steady_clock::now();
     // ---- layout of the upload block ----
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
@@ -558,6 +561,7 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
     a.job_flags = (uint8_t*)s.d_flags.p;
     a.job_flag_base = 0;
 
+    const auto t_packed = std::chrono::steady_clock::now();
     CUDA_TRY(cudaMemcpyAsync(s.d_in.p, s.h_in.p, in_bytes, cudaMemcpyHostToDevice, s.stream));
     p.h2d_bytes = in_bytes;
     if (!do_launch) return PHMM_OK;
@@ -567,6 +571,12 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
     CUDA_TRY(cudaMemcpyAsync(s.h_out.p, s.d_out.p, out_bytes, cudaMemcpyDeviceToHost, s.stream));
     CUDA_TRY(cudaEventRecord(s.ev_done, s.stream));
     p.d2h_bytes = out_bytes;
+    if (trace) {
+        const auto t_end = std::chrono::steady_clock::now();
+        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "phmm trace: stage plan %.3f ms, pack %.3f ms, launch %.3f ms (%d jobs, %d launches, %lld pairs)\n",
+                ms(t_begin, t_planned), ms(t_planned, t_packed), ms(t_packed, t_end), p.n_jobs, p.launches, (long long)p.n_pairs);
+    }
     return PHMM_OK;
 }
 
@@ -574,9 +584,12 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
 int finalize_part(phmm_engine* e, DeviceCtx& dc, Slot& s, phmm_result* r, std::string& err)
 {
     (void)dc;
+    static const bool trace = getenv("PHMM_TRACE") != nullptr;
     Part& p = s.part;
     if (p.n_pairs == 0) return PHMM_OK;
+    const auto t_begin = std::chrono::steady_clock::now();
     CUDA_TRY(cudaEventSynchronize(s.ev_done));
+    const auto t_synced = std::chrono::steady_clock::now();
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1));
     p.kernel_ms = ms;
@@ -642,6 +655,12 @@ int finalize_part(phmm_engine* e, DeviceCtx& dc, Slot& s, phmm_result* r, std::s
         out[i] = std::log10(d) - T.log10_init_d;                     // :139
         if (o64) o64[i] = d;
         if (ores) ores[i] = 1;
+    }
+    if (trace) {
+        const auto t_end = std::chrono::steady_clock::now();
+        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "phmm trace: finalize wait %.3f ms, log10 + rescue %.3f ms (kernels %.3f ms)\n",
+                ms(t_begin, t_synced), ms(t_synced, t_end), p.kernel_ms);
     }
     return PHMM_OK;
 }
