@@ -136,6 +136,7 @@ struct Part {
     int n_jobs = 0;
     int job_beg[2 * kNumShapes + 1] = {0};  // jobs are grouped by kernel slot = shape + kNumShapes * aligned
     int haps_per_job = 1, hap_chunks = 1;
+    int haps_per_job64 = 1, hap_chunks64 = 1;    // chunking of the FP64 redo launches (see stage_and_launch)
     size_t h2d_bytes = 0, d2h_bytes = 0;
     int launches = 0;
     float kernel_ms = 0.f;
@@ -162,6 +163,7 @@ struct phmm_engine_impl;
 struct DeviceCtx {
     int ordinal = 0;
     int sm_count = 148;
+    float last_rescue_frac = 0.f;        // share of pairs the previous batch redid in FP64
     std::vector<Slot> slots;
     int next_slot = 0;
     float* d_ph2pr_f = nullptr; float* d_mm_f = nullptr;
@@ -326,8 +328,11 @@ int launch_kernels(Slot& s, bool exact, int tier_lo, int tier_hi, std::string& e
         ak.n_jobs = n;
         ak.job_flag_base = p.job_beg[k];
         ak.smem_bytes_per_warp = per_warp;
-        dim3 grid((n + kWarpsPerCta - 1) / kWarpsPerCta, p.hap_chunks);
+        ak.flag_hpj = p.haps_per_job;
+        ak.flag_chunks = p.hap_chunks;
         for (int tier = tier_lo; tier <= tier_hi; tier++) {       // tier 3 runs the EXACT FP64 kernel
+            ak.haps_per_job = tier == 1 ? p.haps_per_job : p.haps_per_job64;
+            dim3 grid((n + kWarpsPerCta - 1) / kWarpsPerCta, tier == 1 ? p.hap_chunks : p.hap_chunks64);
             KernelFn fn = kernel_table().fn[tier >= 2][(exact || tier == 3) ? 1 : 0][p.mode][k / kNumShapes][k % kNumShapes];
             ak.tier = tier;
             if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -462,6 +467,14 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
         hpj = std::min(hpj, by_smem);
         p.haps_per_job = hpj;
         p.hap_chunks = (nhm + hpj - 1) / hpj;
+        // FP64 redo: when few pairs underflow (the normal case), a poorly matching read underflows against
+        // every haplotype of its chunk, and one warp redoing them one after the other is the critical path
+        // of the whole launch -- so the redo cuts the haplotypes one per warp (warps without work exit on a
+        // flag byte).  When most pairs are redone (long reads with low-quality tails) the coarse chunks
+        // amortise setup and fill better; the choice follows the device's previous batch.
+        const bool dense = dc.last_rescue_frac > 0.05f;
+        p.haps_per_job64 = dense ? hpj : 1;
+        p.hap_chunks64 = (nhm + p.haps_per_job64 - 1) / p.haps_per_job64;
     }
 
     const auto t_planned = std::chrono::steady_clock::now();
@@ -583,7 +596,6 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
 // Wait for the slot, fetch the rescue list if any, convert raw sums to log10 (intel_pairhmm.hpp:137-143).
 int finalize_part(phmm_engine* e, DeviceCtx& dc, Slot& s, phmm_result* r, std::string& err)
 {
-    (void)dc;
     static const bool trace = getenv("PHMM_TRACE") != nullptr;
     Part& p = s.part;
     if (p.n_pairs == 0) return PHMM_OK;
@@ -635,6 +647,7 @@ int finalize_part(phmm_engine* e, DeviceCtx& dc, Slot& s, phmm_result* r, std::s
         if (count > (uint64_t)p.n_pairs) { err = "rescue counter overflow"; return PHMM_ERR_CUDA; }
     }
     p.rescue_count = count;
+    dc.last_rescue_frac = (float)((double)count / (double)p.n_pairs);
     if (count) {
         CUDA_TRY(s.h_rescue.reserve(sizeof(RescueOut) * (size_t)count));
         CUDA_TRY(cudaMemcpyAsync(s.h_rescue.p, s.d_rescue.p, sizeof(RescueOut) * (size_t)count, cudaMemcpyDeviceToHost, s.stream));

@@ -116,6 +116,8 @@ struct KernelArgs {
     uint8_t*   job_flags;                // [n_jobs_total * hap_chunks]: 1 = some pair of this (job, chunk)
                                          // underflowed in FP32, so the FP64 kernel has work there
     int32_t    job_flag_base;            // index of this launch's first job in job_flags
+    int32_t    flag_hpj, flag_chunks;    // chunking of the FLAGS = the FP32 launch's haps_per_job and grid.y; an
+                                         // FP64 launch may cut the haplotypes finer (its own haps_per_job)
     int32_t    tier;                     // FP64 launches: 2 = redo of FP32 underflows, 3 = flush-exact redo of the
                                          // pairs whose FP64 sum came out within reach of the denormal range
 };
@@ -281,8 +283,11 @@ forward_kernel(const KernelArgs args)
     const int job_idx = blockIdx.x * kWarpsPerCta + warp;
     if (job_idx >= args.n_jobs) return;
 
-    uint8_t* const my_flag = args.job_flags + ((size_t)(args.job_flag_base + job_idx) * gridDim.y + blockIdx.y);
-    if (!P::kIsF32 && *my_flag != (args.tier == 3 ? 2 : 1)) return;   // nothing to redo here: one byte read, done
+    uint8_t* const my_flag = args.job_flags + ((size_t)(args.job_flag_base + job_idx) * args.flag_chunks +
+                                               (blockIdx.y * args.haps_per_job) / args.flag_hpj);
+    // nothing to redo here: one byte read, done.  (Several FP64 warps may share a flag byte, and one of them
+    // may already have raised it to 2 for tier 3, so tier 2 only tests for non-zero.)
+    if (!P::kIsF32 && (args.tier == 3 ? *my_flag != 2 : *my_flag == 0)) return;
     // FP64: which pairs this launch redoes, told from their raw FP32 sum
     auto needs_redo = [&](const float raw) {
         return args.tier == 3 ? (__float_as_uint(raw) >> 31) != 0u : raw < kMinAccepted;
