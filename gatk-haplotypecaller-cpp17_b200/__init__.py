@@ -71,7 +71,8 @@ class _Result(C.Structure):
 
 EXPORTS = ["phmm_create", "phmm_destroy", "phmm_compute", "phmm_submit", "phmm_wait", "phmm_strerror",
            "phmm_last_error", "phmm_abi_version", "phmm_normalize_filter", "phmm_tables",
-           "phmm_stage", "phmm_run_staged", "phmm_fetch_staged", "phmm_free_staged"]
+           "phmm_stage", "phmm_run_staged", "phmm_run_staged_ex", "phmm_run_staged_pipelined",
+           "phmm_fetch_staged", "phmm_free_staged"]
 
 _lib = None
 
@@ -96,6 +97,10 @@ def lib():
                                   C.POINTER(C.c_int32)]
         L.phmm_stage.argtypes = [C.c_void_p, C.POINTER(_Batch), C.POINTER(C.c_void_p)]
         L.phmm_run_staged.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
+        L.phmm_run_staged_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                         C.POINTER(C.c_int32)]
+        L.phmm_run_staged_pipelined.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int32,
+                                                C.POINTER(C.c_float), C.POINTER(C.c_int32)]
         L.phmm_fetch_staged.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_Result)]
         L.phmm_free_staged.argtypes = [C.c_void_p, C.c_void_p]; L.phmm_free_staged.restype = None
         _lib = L
@@ -307,6 +312,19 @@ class PairHMMEngine:
     def run_staged(self, st, iters=1):
         ms, n = C.c_float(), C.c_int32()
         self._check(self._L.phmm_run_staged(self._h, st, iters, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def run_staged_ex(self, st, iters=1):
+        """(ms per pass, ms of the FP32 forward launch alone or -1, launches per pass)"""
+        ms, ms32, n = C.c_float(), C.c_float(), C.c_int32()
+        self._check(self._L.phmm_run_staged_ex(self._h, st, iters, C.byref(ms), C.byref(ms32), C.byref(n)))
+        return ms.value, ms32.value, n.value
+
+    def run_staged_pipelined(self, staged, steps):
+        """`steps` passes, step i on staged[i % n], each batch on its own stream; (total device ms, launches)"""
+        arr = (C.c_void_p * len(staged))(*[s.value for s in staged])
+        ms, n = C.c_float(), C.c_int32()
+        self._check(self._L.phmm_run_staged_pipelined(self._h, arr, len(staged), steps, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
     def fetch_staged(self, st, n_pairs, want_raw=True):

@@ -150,6 +150,8 @@ struct Slot {
     cudaStream_t aux[kAuxStreams] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[kAuxStreams] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_k32 = nullptr;            // after the FP32 launch of a single-shape batch (dominant-kernel timing)
+    bool k32_valid = false;
     PinnedBuf h_in, h_out, h_rescue;
     DeviceBuf d_in, d_out, d_rescue, d_flags;
     bool busy = false;
@@ -302,6 +304,7 @@ int launch_kernels(Slot& s, bool exact, int tier_lo, int tier_hi, std::string& e
     const KernelArgs& a = s.args;
     if (tier_lo == 1) {
         p.launches = 0;
+        s.k32_valid = false;
         CUDA_TRY(cudaMemsetAsync(s.d_out.p, 0, 16, s.stream));
         CUDA_TRY(cudaMemsetAsync(s.d_flags.p, 0, (size_t)p.n_jobs * p.hap_chunks, s.stream));
         CUDA_TRY(cudaEventRecord(s.ev_k0, s.stream));
@@ -339,6 +342,7 @@ int launch_kernels(Slot& s, bool exact, int tier_lo, int tier_hi, std::string& e
             fn<<<grid, kWarpsPerCta * 32, smem, st>>>(ak);
             CUDA_TRY(cudaGetLastError());
             p.launches++;
+            if (tier == 1 && !fork) { CUDA_TRY(cudaEventRecord(s.ev_k32, st)); s.k32_valid = true; }
         }
     }
     if (fork)
@@ -688,6 +692,7 @@ int init_slot(Slot& s, std::string& err)
     CUDA_TRY(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreate(&s.ev_k0));
     CUDA_TRY(cudaEventCreate(&s.ev_k1));
+    CUDA_TRY(cudaEventCreate(&s.ev_k32));
     CUDA_TRY(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
     return PHMM_OK;
 }
@@ -727,6 +732,7 @@ void free_slot(Slot& s)
     if (s.ev_fork) cudaEventDestroy(s.ev_fork);
     if (s.ev_k0) cudaEventDestroy(s.ev_k0);
     if (s.ev_k1) cudaEventDestroy(s.ev_k1);
+    if (s.ev_k32) cudaEventDestroy(s.ev_k32);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
     if (s.stream) cudaStreamDestroy(s.stream);
 }
@@ -983,13 +989,15 @@ int phmm_stage(phmm_engine* e, const phmm_batch* b, phmm_staged** out)
     return PHMM_OK;
 }
 
-int phmm_run_staged(phmm_engine* e, phmm_staged* st, int32_t iters, float* ms_per_iter, int32_t* launches_per_iter)
+int phmm_run_staged_ex(phmm_engine* e, phmm_staged* st, int32_t iters, float* ms_per_iter, float* fp32_ms_per_iter,
+                       int32_t* launches_per_iter)
 {
     if (!e || !st || iters < 1) return PHMM_ERR_INVALID_ARG;
     DeviceCtx& dc = *e->devs[0];
     std::string err;
     int rc = PHMM_OK;
-    float ms = 0.f;
+    float ms = 0.f, ms32 = 0.f;
+    bool have32 = true;
     int launches = 0;
     Latch latch(1);
     dc.post([&] {
@@ -1006,6 +1014,8 @@ int phmm_run_staged(phmm_engine* e, phmm_staged* st, int32_t iters, float* ms_pe
                 float one = 0.f;
                 CUDA_TRY(cudaEventElapsedTime(&one, s.ev_k0, s.ev_k1));
                 ms += one;
+                if (s.k32_valid) { CUDA_TRY(cudaEventElapsedTime(&one, s.ev_k0, s.ev_k32)); ms32 += one; }
+                else have32 = false;
                 launches = p.launches;
             }
             return PHMM_OK;
@@ -1018,7 +1028,60 @@ int phmm_run_staged(phmm_engine* e, phmm_staged* st, int32_t iters, float* ms_pe
     st->ran = true;
     st->slot.part.launches = launches;
     if (ms_per_iter) *ms_per_iter = ms / iters;
+    if (fp32_ms_per_iter) *fp32_ms_per_iter = have32 ? ms32 / iters : -1.f;
     if (launches_per_iter) *launches_per_iter = launches;
+    return PHMM_OK;
+}
+
+int phmm_run_staged(phmm_engine* e, phmm_staged* st, int32_t iters, float* ms_per_iter, int32_t* launches_per_iter)
+{
+    return phmm_run_staged_ex(e, st, iters, ms_per_iter, nullptr, launches_per_iter);
+}
+
+int phmm_run_staged_pipelined(phmm_engine* e, phmm_staged* const* sts, int32_t n, int32_t steps, float* total_ms,
+                              int32_t* launches)
+{
+    if (!e || !sts || n < 1 || steps < 1) return PHMM_ERR_INVALID_ARG;
+    for (int i = 0; i < n; i++) if (!sts[i]) return PHMM_ERR_INVALID_ARG;
+    DeviceCtx& dc = *e->devs[0];
+    std::string err;
+    int rc = PHMM_OK;
+    float ms = 0.f;
+    int nl = 0;
+    Latch latch(1);
+    dc.post([&] {
+        const bool exact = e->opt.exact_fp32 != 0;
+        auto go = [&]() -> int {
+            // Step i runs on the stream of staged batch i % n: consecutive steps overlap (one batch's FP64 redo
+            // and tail with the next batch's FP32 kernel), a batch's own steps stay in order.  Timed from a
+            // start event every stream waits on to an end event that waits on every stream.
+            Slot& s0 = sts[0]->slot;
+            cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+            CUDA_TRY(cudaEventCreate(&ev_begin));
+            CUDA_TRY(cudaEventCreate(&ev_end));
+            CUDA_TRY(cudaEventRecord(ev_begin, s0.stream));
+            for (int i = 1; i < std::min(n, steps); i++) CUDA_TRY(cudaStreamWaitEvent(sts[i]->slot.stream, ev_begin, 0));
+            for (int it = 0; it < steps; it++) {
+                Slot& s = sts[it % n]->slot;
+                int rc2 = launch_kernels(s, exact, 1, 2, err);
+                if (rc2) return rc2;
+                nl += s.part.launches;
+            }
+            for (int i = 1; i < std::min(n, steps); i++) CUDA_TRY(cudaStreamWaitEvent(s0.stream, sts[i]->slot.ev_k1, 0));
+            CUDA_TRY(cudaEventRecord(ev_end, s0.stream));
+            CUDA_TRY(cudaEventSynchronize(ev_end));
+            CUDA_TRY(cudaEventElapsedTime(&ms, ev_begin, ev_end));
+            cudaEventDestroy(ev_begin); cudaEventDestroy(ev_end);
+            return PHMM_OK;
+        };
+        rc = go();
+        latch.done();
+    });
+    latch.wait();
+    if (rc) { e->set_error(err); return rc; }
+    for (int i = 0; i < std::min(n, steps); i++) sts[i]->ran = true;
+    if (total_ms) *total_ms = ms;
+    if (launches) *launches = nl;
     return PHMM_OK;
 }
 

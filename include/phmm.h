@@ -148,6 +148,16 @@ typedef struct phmm_staged phmm_staged;
 int  phmm_stage(phmm_engine* e, const phmm_batch* b, phmm_staged** out);
 int  phmm_run_staged(phmm_engine* e, phmm_staged* s, int32_t iters, float* ms_per_iter,
                      int32_t* launches_per_iter);
+/* As phmm_run_staged; additionally the mean device time of the FP32 forward launch alone (the dominant
+ * kernel, bracketed by events on its stream), or -1 when the batch needs several shapes (forked streams). */
+int  phmm_run_staged_ex(phmm_engine* e, phmm_staged* s, int32_t iters, float* ms_per_iter,
+                        float* fp32_ms_per_iter, int32_t* launches_per_iter);
+/* `steps` passes over n staged batches, step i on batch i % n, each batch on its own stream so that
+ * consecutive steps overlap (one batch's FP64 redo and kernel tail with the next batch's FP32 kernel), as
+ * they do behind phmm_submit with several tickets in flight.  total_ms: device time from a start event
+ * every stream waits on to an end event that waits on every stream; launches: kernels launched. */
+int  phmm_run_staged_pipelined(phmm_engine* e, phmm_staged* const* staged, int32_t n, int32_t steps,
+                               float* total_ms, int32_t* launches);
 int  phmm_fetch_staged(phmm_engine* e, phmm_staged* s, phmm_result* r);
 void phmm_free_staged(phmm_engine* e, phmm_staged* s);
 
