@@ -396,47 +396,29 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
     p.mode = !constant ? kModeGeneral : (((p.gap[0] & 127) == (p.gap[1] & 127)) ? kModeConstShared : kModeConst);
     const bool general = p.mode == kModeGeneral;
 
-    // ---- plan: per region, reads that share a shape are scored 2 per lane group, 32/G groups per warp ----
+    // ---- plan: per region, reads sorted by length and cut into warp jobs (2 reads per lane group, 32/G
+    //      groups per warp); the job's shape is the one its LONGEST read asks for.  Sorting keeps the
+    //      reads of a job within a few bases of each other (few dummy rows) and leaves one partial job per
+    //      region instead of one per shape: on the reference's windows, where half of the reads are
+    //      clipped to 10..149 bases, that is ~14% fewer jobs than grouping by each read's own shape. ----
     constexpr int kSlots = 2 * kNumShapes;
     auto is_aligned = [&](int R, int sh) {
         return !general && (R % kShapes[sh].K == 0) && (kShapes[sh].K * kShapes[sh].G - R >= kShapes[sh].K);
     };
-    bool use_aligned[kNumShapes];
-    {
-        int64_t n_al[kNumShapes] = {0}, n_all[kNumShapes] = {0};
-        for (int g = g0; g < g1; g++) {
-            const int nh = b->region_hap_beg[g + 1] - b->region_hap_beg[g];
-            if (nh == 0) continue;
-            const int h_avg = (int)((b->hap_off[b->region_hap_beg[g + 1]] - b->hap_off[b->region_hap_beg[g]]) / nh);
-            for (int r = b->region_read_beg[g]; r < b->region_read_beg[g + 1]; r++) {
-                const int R = b->read_off[r + 1] - b->read_off[r];
-                if (R > kMaxReadLenCompiled) continue;
-                const int sh = pick_shape(R, h_avg);
-                n_all[sh]++; n_al[sh] += is_aligned(R, sh);
-            }
-        }
-        for (int sh = 0; sh < kNumShapes; sh++) use_aligned[sh] = n_al[sh] * 10 >= n_all[sh] * 9;
-    }
-    std::vector<WarpJob> jobs_k[kSlots];
+    struct PlannedJob { WarpJob job; int shape; bool aligned; };
+    std::vector<PlannedJob> planned;
     std::vector<LongPair> long_pairs;
+    std::vector<std::pair<int, int>> by_len;         // (read length, read index within the part)
+    int64_t n_jobs_sh[kNumShapes] = {0}, n_aligned_sh[kNumShapes] = {0};
     int64_t out_acc = 0;                     // first output index of region g within this part
     for (int g = g0; g < g1; out_acc += (int64_t)(b->region_read_beg[g + 1] - b->region_read_beg[g]) *
                                         (b->region_hap_beg[g + 1] - b->region_hap_beg[g]), g++) {
-        WarpJob pending[kSlots];
-        int n_pending[kSlots];
-        for (int k = 0; k < kSlots; k++) n_pending[k] = 0;
         const int nh = b->region_hap_beg[g + 1] - b->region_hap_beg[g];
         p.max_nh = std::max(p.max_nh, nh);
         if (nh == 0) continue;
         const int64_t hap_sum = b->hap_off[b->region_hap_beg[g + 1]] - b->hap_off[b->region_hap_beg[g]];
         const int h_avg = (int)(hap_sum / nh);
-        auto flush = [&](int k) {
-            WarpJob& j = pending[k];
-            j.region = g - g0;
-            for (int q = n_pending[k]; q < kMaxJobReads; q++) j.read[q] = -1;
-            jobs_k[k].push_back(j);
-            n_pending[k] = 0;
-        };
+        by_len.clear();
         for (int r = b->region_read_beg[g]; r < b->region_read_beg[g + 1]; r++) {
             const int R = b->read_off[r + 1] - b->read_off[r];
             p.n_cells += (int64_t)R * hap_sum;
@@ -446,29 +428,64 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
                                           out_acc + (int64_t)(r - b->region_read_beg[g]) * nh + h});
                 continue;
             }
-            const int sh = pick_shape(R, h_avg);
-            // lane-aligned reads (length a multiple of K, at least K dummy rows) take the ALIGNED kernels,
-            // provided most reads of that shape do (otherwise the split only fragments the launches)
-            const bool aligned = use_aligned[sh] && is_aligned(R, sh);
-            const int k = sh + (aligned ? kNumShapes : 0);
-            pending[k].read[n_pending[k]++] = r - r0;
-            if (n_pending[k] == 2 * (32 / kShapes[sh].G)) flush(k);
+            by_len.emplace_back(R, r - r0);
         }
-        for (int k = 0; k < kSlots; k++) if (n_pending[k]) flush(k);
+        std::sort(by_len.begin(), by_len.end(), [](const std::pair<int, int>& x, const std::pair<int, int>& y) {
+            return x.first != y.first ? x.first > y.first : x.second < y.second;
+        });
+        for (size_t i = 0; i < by_len.size();) {
+            const int sh = pick_shape(by_len[i].first, h_avg);
+            const int cap = 2 * (32 / kShapes[sh].G);
+            PlannedJob pj;
+            pj.shape = sh; pj.aligned = true;
+            pj.job.region = g - g0;
+            int q = 0;
+            for (; q < cap && i < by_len.size(); q++, i++) {
+                pj.job.read[q] = by_len[i].second;
+                pj.aligned = pj.aligned && is_aligned(by_len[i].first, sh);
+            }
+            for (; q < kMaxJobReads; q++) pj.job.read[q] = -1;
+            n_jobs_sh[sh]++; n_aligned_sh[sh] += pj.aligned;
+            planned.push_back(pj);
+        }
+    }
+    // Jobs whose reads are all a whole number of lanes take the ALIGNED kernels -- provided enough jobs of
+    // that shape do (otherwise the split only adds small launches).
+    std::vector<WarpJob> jobs_k[kSlots];
+    for (const PlannedJob& pj : planned) {
+        const bool use_al = pj.aligned && n_aligned_sh[pj.shape] * 10 >= n_jobs_sh[pj.shape] && n_aligned_sh[pj.shape] >= 32;
+        jobs_k[pj.shape + (use_al ? kNumShapes : 0)].push_back(pj.job);
     }
     for (int h = h0; h < h1; h++) p.max_H = std::max(p.max_H, b->hap_off[h + 1] - b->hap_off[h]);
     p.n_jobs = 0;
     for (int k = 0; k < kSlots; k++) { p.job_beg[k] = p.n_jobs; p.n_jobs += (int)jobs_k[k].size(); }
     p.job_beg[kSlots] = p.n_jobs;
-    {   // Haplotypes streamed per (job, chunk): as many as possible (the wavefront fills and drains
-        // once per chunk), but enough (job, chunk) units to fill the chip ~8 times over, and a
-        // stream that fits the per-warp shared-memory budget.
-        const int64_t target = (int64_t)dc.sm_count * 16 * 8;
+    {   // Haplotypes streamed per (job, chunk).  More per chunk: the wavefront fills and drains once per
+        // chunk and the per-job setup (prior tables) is paid once.  Fewer: more independent units, and a
+        // bounded longest unit -- a launch is over when its longest warp is, and a region with 16 haplotypes
+        // in a stream of 2-haplotype regions would otherwise run 8x longer than the rest (measured on the
+        // ragged window stream: single-shape kernels took one such job's duration).  Makespan model over the
+        // candidates: all steps / resident warps + the longest unit; overhead per chunk ~128 steps.
         const int nhm = std::max(1, p.max_nh);
-        int chunks = (int)std::min<int64_t>(std::max<int64_t>(1, (target + p.n_jobs - 1) / std::max(1, p.n_jobs)), nhm);
-        int hpj = (nhm + chunks - 1) / chunks;
         const int by_smem = std::max(1, (kSmemBytesPerWarpBudget - 2 * (kSkew * 31 + 3) - 16) / (p.max_H + 1 + kPerHapTableBytes));
-        hpj = std::min(hpj, by_smem);
+        std::vector<int64_t> jobs_with_nh(nhm + 1, 0);
+        for (const PlannedJob& pj : planned) {
+            const int g = g0 + pj.job.region;
+            jobs_with_nh[b->region_hap_beg[g + 1] - b->region_hap_beg[g]]++;
+        }
+        const double h_mean = p.n_haps ? (double)hap_bytes / p.n_haps : 1.0;
+        const double resident = (double)dc.sm_count * 12;
+        constexpr double kChunkOverheadSteps = 128;   // calibrated on S3: 4 haplotypes per chunk beat 2 by 1%
+        static const int force_hpj = [] { const char* s = getenv("PHMM_FORCE_HPJ"); return s ? atoi(s) : 0; }();
+        int best_hpj = 1; double best_t = 0;
+        for (int hpj = 1; hpj <= std::min(nhm, by_smem); hpj++) {
+            double steps = 0;
+            for (int n = 1; n <= nhm; n++)
+                if (jobs_with_nh[n]) steps += (double)jobs_with_nh[n] * (n * (h_mean + 1) + ((n + hpj - 1) / hpj) * kChunkOverheadSteps);
+            const double t = steps / resident + hpj * (double)(p.max_H + 1) + kChunkOverheadSteps;
+            if (hpj == 1 || t <= best_t) { best_t = t; best_hpj = hpj; }
+        }
+        int hpj = force_hpj > 0 ? std::min(force_hpj, std::min(nhm, by_smem)) : best_hpj;
         p.haps_per_job = hpj;
         p.hap_chunks = (nhm + hpj - 1) / hpj;
         // FP64 redo: when few pairs underflow (the normal case), a poorly matching read underflows against
