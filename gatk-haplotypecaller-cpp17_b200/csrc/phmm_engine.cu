@@ -124,6 +124,67 @@ struct DeviceBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// ---- host-side parallel_for: planning, packing and the log10 pass of a batch are spread over the
+//      engine's host_threads (per device: host_threads - 1 workers + the device's own worker thread) ----
+class HostPool {
+public:
+    explicit HostPool(int n_workers) {
+        for (int i = 0; i < n_workers; i++) th_.emplace_back([this] { loop(); });
+    }
+    ~HostPool() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    int width() const { return (int)th_.size() + 1; }
+    // fn(i) for i in [0, n), on the workers and the calling thread; returns when all are done
+    void parallel_for(int n, const std::function<void(int)>& fn) {
+        if (n <= 0) return;
+        if (n == 1 || th_.empty()) { for (int i = 0; i < n; i++) fn(i); return; }
+        auto task = std::make_shared<Task>();
+        task->fn = fn; task->total = n;
+        { std::lock_guard<std::mutex> lk(mu_); cur_ = task; ++generation_; }
+        cv_.notify_all();
+        run(*task);
+        std::unique_lock<std::mutex> lk(task->mu);
+        task->cv.wait(lk, [&] { return task->done.load() == task->total; });
+    }
+private:
+    struct Task {
+        std::function<void(int)> fn;
+        int total = 0;
+        std::atomic<int> next{0}, done{0};
+        std::mutex mu; std::condition_variable cv;
+    };
+    static void run(Task& t) {
+        for (;;) {
+            const int i = t.next.fetch_add(1);
+            if (i >= t.total) return;
+            t.fn(i);
+            if (t.done.fetch_add(1) + 1 == t.total) { std::lock_guard<std::mutex> lk(t.mu); t.cv.notify_all(); }
+        }
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            std::shared_ptr<Task> task;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || generation_ != seen; });
+                if (stop_) return;
+                seen = generation_;
+                task = cur_;
+            }
+            if (task) run(*task);
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex mu_; std::condition_variable cv_;
+    std::shared_ptr<Task> cur_;
+    uint64_t generation_ = 0;
+    bool stop_ = false;
+};
+
 // ---- one device's share of a batch: a contiguous range of regions -----------------------------
 struct Part {
     int g0 = 0, g1 = 0;                       // region range in the caller's batch
@@ -166,6 +227,7 @@ struct DeviceCtx {
     int ordinal = 0;
     int sm_count = 148;
     float last_rescue_frac = 0.f;        // share of pairs the previous batch redid in FP64
+    std::unique_ptr<HostPool> pool;      // host_threads - 1 helpers for this device's worker thread
     std::vector<Slot> slots;
     int next_slot = 0;
     float* d_ph2pr_f = nullptr; float* d_mm_f = nullptr;
@@ -406,56 +468,88 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
         return !general && (R % kShapes[sh].K == 0) && (kShapes[sh].K * kShapes[sh].G - R >= kShapes[sh].K);
     };
     struct PlannedJob { WarpJob job; int shape; bool aligned; };
-    std::vector<PlannedJob> planned;
+    // first output index of every region within this part (also uploaded: region_out_beg)
+    std::vector<int64_t> out_beg(p.n_regions + 1, 0);
+    for (int g = g0; g < g1; g++)
+        out_beg[g - g0 + 1] = out_beg[g - g0] + (int64_t)(b->region_read_beg[g + 1] - b->region_read_beg[g]) *
+                                                    (b->region_hap_beg[g + 1] - b->region_hap_beg[g]);
+    struct PlanPiece {                       // one contiguous range of regions, planned by one host thread
+        std::vector<PlannedJob> planned;
+        std::vector<LongPair> long_pairs;
+        int64_t n_cells = 0;
+        int max_nh = 0;
+        int64_t n_jobs_sh[kNumShapes] = {0}, n_aligned_sh[kNumShapes] = {0};
+    };
+    HostPool& pool = *dc.pool;
+    const int n_pieces = std::max(1, std::min(pool.width(), p.n_reads / 4096));
+    std::vector<PlanPiece> pieces(n_pieces);
+    std::vector<int> piece_cut(n_pieces + 1, g1);
+    piece_cut[0] = g0;
+    for (int t = 1, g = g0; t < n_pieces; t++) {           // cut by read count
+        const int64_t want = r0 + (int64_t)p.n_reads * t / n_pieces;
+        while (g < g1 && b->region_read_beg[g] < want) g++;
+        piece_cut[t] = g;
+    }
+    pool.parallel_for(n_pieces, [&](int t) {
+        PlanPiece& pc = pieces[t];
+        std::vector<std::pair<int, int>> by_len;         // (read length, read index within the part)
+        for (int g = piece_cut[t]; g < piece_cut[t + 1]; g++) {
+            const int nh = b->region_hap_beg[g + 1] - b->region_hap_beg[g];
+            pc.max_nh = std::max(pc.max_nh, nh);
+            if (nh == 0) continue;
+            const int64_t hap_sum = b->hap_off[b->region_hap_beg[g + 1]] - b->hap_off[b->region_hap_beg[g]];
+            const int h_avg = (int)(hap_sum / nh);
+            by_len.clear();
+            for (int r = b->region_read_beg[g]; r < b->region_read_beg[g + 1]; r++) {
+                const int R = b->read_off[r + 1] - b->read_off[r];
+                pc.n_cells += (int64_t)R * hap_sum;
+                if (R > kMaxReadLenCompiled) {   // beyond one lane-group pass: phmm_long.cu, one warp per pair
+                    for (int h = 0; h < nh; h++)
+                        pc.long_pairs.push_back({r - r0, b->region_hap_beg[g] - h0 + h,
+                                                 out_beg[g - g0] + (int64_t)(r - b->region_read_beg[g]) * nh + h});
+                    continue;
+                }
+                by_len.emplace_back(R, r - r0);
+            }
+            std::sort(by_len.begin(), by_len.end(), [](const std::pair<int, int>& x, const std::pair<int, int>& y) {
+                return x.first != y.first ? x.first > y.first : x.second < y.second;
+            });
+            for (size_t i = 0; i < by_len.size();) {
+                const int sh = pick_shape(by_len[i].first, h_avg);
+                const int cap = 2 * (32 / kShapes[sh].G);
+                PlannedJob pj;
+                pj.shape = sh; pj.aligned = true;
+                pj.job.region = g - g0;
+                int q = 0;
+                for (; q < cap && i < by_len.size(); q++, i++) {
+                    pj.job.read[q] = by_len[i].second;
+                    pj.aligned = pj.aligned && is_aligned(by_len[i].first, sh);
+                }
+                for (; q < kMaxJobReads; q++) pj.job.read[q] = -1;
+                pc.n_jobs_sh[sh]++; pc.n_aligned_sh[sh] += pj.aligned;
+                pc.planned.push_back(pj);
+            }
+        }
+    });
     std::vector<LongPair> long_pairs;
-    std::vector<std::pair<int, int>> by_len;         // (read length, read index within the part)
     int64_t n_jobs_sh[kNumShapes] = {0}, n_aligned_sh[kNumShapes] = {0};
-    int64_t out_acc = 0;                     // first output index of region g within this part
-    for (int g = g0; g < g1; out_acc += (int64_t)(b->region_read_beg[g + 1] - b->region_read_beg[g]) *
-                                        (b->region_hap_beg[g + 1] - b->region_hap_beg[g]), g++) {
-        const int nh = b->region_hap_beg[g + 1] - b->region_hap_beg[g];
-        p.max_nh = std::max(p.max_nh, nh);
-        if (nh == 0) continue;
-        const int64_t hap_sum = b->hap_off[b->region_hap_beg[g + 1]] - b->hap_off[b->region_hap_beg[g]];
-        const int h_avg = (int)(hap_sum / nh);
-        by_len.clear();
-        for (int r = b->region_read_beg[g]; r < b->region_read_beg[g + 1]; r++) {
-            const int R = b->read_off[r + 1] - b->read_off[r];
-            p.n_cells += (int64_t)R * hap_sum;
-            if (R > kMaxReadLenCompiled) {       // beyond one lane-group pass: phmm_long.cu, one warp per pair
-                for (int h = 0; h < nh; h++)
-                    long_pairs.push_back({r - r0, b->region_hap_beg[g] - h0 + h,
-                                          out_acc + (int64_t)(r - b->region_read_beg[g]) * nh + h});
-                continue;
-            }
-            by_len.emplace_back(R, r - r0);
-        }
-        std::sort(by_len.begin(), by_len.end(), [](const std::pair<int, int>& x, const std::pair<int, int>& y) {
-            return x.first != y.first ? x.first > y.first : x.second < y.second;
-        });
-        for (size_t i = 0; i < by_len.size();) {
-            const int sh = pick_shape(by_len[i].first, h_avg);
-            const int cap = 2 * (32 / kShapes[sh].G);
-            PlannedJob pj;
-            pj.shape = sh; pj.aligned = true;
-            pj.job.region = g - g0;
-            int q = 0;
-            for (; q < cap && i < by_len.size(); q++, i++) {
-                pj.job.read[q] = by_len[i].second;
-                pj.aligned = pj.aligned && is_aligned(by_len[i].first, sh);
-            }
-            for (; q < kMaxJobReads; q++) pj.job.read[q] = -1;
-            n_jobs_sh[sh]++; n_aligned_sh[sh] += pj.aligned;
-            planned.push_back(pj);
-        }
+    size_t n_planned = 0;
+    for (const PlanPiece& pc : pieces) {
+        p.n_cells += pc.n_cells;
+        p.max_nh = std::max(p.max_nh, pc.max_nh);
+        n_planned += pc.planned.size();
+        long_pairs.insert(long_pairs.end(), pc.long_pairs.begin(), pc.long_pairs.end());
+        for (int sh = 0; sh < kNumShapes; sh++) { n_jobs_sh[sh] += pc.n_jobs_sh[sh]; n_aligned_sh[sh] += pc.n_aligned_sh[sh]; }
     }
     // Jobs whose reads are all a whole number of lanes take the ALIGNED kernels -- provided enough jobs of
     // that shape do (otherwise the split only adds small launches).
     std::vector<WarpJob> jobs_k[kSlots];
-    for (const PlannedJob& pj : planned) {
-        const bool use_al = pj.aligned && n_aligned_sh[pj.shape] * 10 >= n_jobs_sh[pj.shape] && n_aligned_sh[pj.shape] >= 32;
-        jobs_k[pj.shape + (use_al ? kNumShapes : 0)].push_back(pj.job);
-    }
+    for (const PlanPiece& pc : pieces)
+        for (const PlannedJob& pj : pc.planned) {
+            const bool use_al = pj.aligned && n_aligned_sh[pj.shape] * 10 >= n_jobs_sh[pj.shape] && n_aligned_sh[pj.shape] >= 32;
+            jobs_k[pj.shape + (use_al ? kNumShapes : 0)].push_back(pj.job);
+        }
+    (void)n_planned;
     for (int h = h0; h < h1; h++) p.max_H = std::max(p.max_H, b->hap_off[h + 1] - b->hap_off[h]);
     p.n_jobs = 0;
     for (int k = 0; k < kSlots; k++) { p.job_beg[k] = p.n_jobs; p.n_jobs += (int)jobs_k[k].size(); }
@@ -469,10 +563,11 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
         const int nhm = std::max(1, p.max_nh);
         const int by_smem = std::max(1, (kSmemBytesPerWarpBudget - 2 * (kSkew * 31 + 3) - 16) / (p.max_H + 1 + kPerHapTableBytes));
         std::vector<int64_t> jobs_with_nh(nhm + 1, 0);
-        for (const PlannedJob& pj : planned) {
-            const int g = g0 + pj.job.region;
-            jobs_with_nh[b->region_hap_beg[g + 1] - b->region_hap_beg[g]]++;
-        }
+        for (const PlanPiece& pc : pieces)
+            for (const PlannedJob& pj : pc.planned) {
+                const int g = g0 + pj.job.region;
+                jobs_with_nh[b->region_hap_beg[g + 1] - b->region_hap_beg[g]]++;
+            }
         const double h_mean = p.n_haps ? (double)hap_bytes / p.n_haps : 1.0;
         const double resident = (double)dc.sm_count * 12;
         constexpr double kChunkOverheadSteps = 128;   // calibrated on S3: 4 haplotypes per chunk beat 2 by 1%
@@ -528,34 +623,40 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
 
     uint8_t* hp = (uint8_t*)s.h_in.p;
     {
-        int32_t* ro = (int32_t*)(hp + o_read_off);
-        for (int r = 0; r <= p.n_reads; r++) ro[r] = b->read_off[r0 + r] - rb0;
-        int32_t* ho = (int32_t*)(hp + o_hap_off);
-        for (int h = 0; h <= p.n_haps; h++) ho[h] = b->hap_off[h0 + h] - hb0;
-        int32_t* rr = (int32_t*)(hp + o_reg_read);
-        int32_t* rh = (int32_t*)(hp + o_reg_hap);
-        int64_t* rout = (int64_t*)(hp + o_reg_out);
-        int64_t acc = 0;
-        for (int g = 0; g <= p.n_regions; g++) {
-            rr[g] = b->region_read_beg[g0 + g] - r0;
-            rh[g] = b->region_hap_beg[g0 + g] - h0;
-            rout[g] = acc;
-            if (g < p.n_regions)
-                acc += (int64_t)(b->region_read_beg[g0 + g + 1] - b->region_read_beg[g0 + g]) *
-                       (b->region_hap_beg[g0 + g + 1] - b->region_hap_beg[g0 + g]);
-        }
-        std::memcpy(hp + o_bases, b->read_bases + rb0, read_bytes);
-        std::memcpy(hp + o_q, b->read_q + rb0, read_bytes);
-        if (general) {
-            std::memcpy(hp + o_gi, b->read_i + rb0, read_bytes);
-            std::memcpy(hp + o_gd, b->read_d + rb0, read_bytes);
-            std::memcpy(hp + o_gc, b->read_c + rb0, read_bytes);
-        }
-        std::memcpy(hp + o_haps, b->hap_bases + hb0, hap_bytes);
-        if (!long_pairs.empty()) std::memcpy(hp + o_long, long_pairs.data(), sizeof(LongPair) * long_pairs.size());
-        WarpJob* jd = (WarpJob*)(hp + o_jobs);
-        for (int k = 0; k < kSlots; k++)
-            if (!jobs_k[k].empty()) std::memcpy(jd + p.job_beg[k], jobs_k[k].data(), sizeof(WarpJob) * jobs_k[k].size());
+        // the byte arrays are cut into one slice per host thread; the small index arrays ride along
+        const int n_slices = std::max(1, std::min(pool.width(), (int)(read_bytes >> 20)));
+        auto slice_copy = [&](size_t dst_off, const uint8_t* src, size_t bytes, int t) {
+            const size_t lo = bytes * t / n_slices, hi = bytes * (t + 1) / n_slices;
+            std::memcpy(hp + dst_off + lo, src + lo, hi - lo);
+        };
+        pool.parallel_for(n_slices + 1, [&](int t) {
+            if (t < n_slices) {
+                slice_copy(o_bases, b->read_bases + rb0, read_bytes, t);
+                slice_copy(o_q, b->read_q + rb0, read_bytes, t);
+                if (general) {
+                    slice_copy(o_gi, b->read_i + rb0, read_bytes, t);
+                    slice_copy(o_gd, b->read_d + rb0, read_bytes, t);
+                    slice_copy(o_gc, b->read_c + rb0, read_bytes, t);
+                }
+                slice_copy(o_haps, b->hap_bases + hb0, hap_bytes, t);
+                return;
+            }
+            int32_t* ro = (int32_t*)(hp + o_read_off);
+            for (int r = 0; r <= p.n_reads; r++) ro[r] = b->read_off[r0 + r] - rb0;
+            int32_t* ho = (int32_t*)(hp + o_hap_off);
+            for (int h = 0; h <= p.n_haps; h++) ho[h] = b->hap_off[h0 + h] - hb0;
+            int32_t* rr = (int32_t*)(hp + o_reg_read);
+            int32_t* rh = (int32_t*)(hp + o_reg_hap);
+            for (int g = 0; g <= p.n_regions; g++) {
+                rr[g] = b->region_read_beg[g0 + g] - r0;
+                rh[g] = b->region_hap_beg[g0 + g] - h0;
+            }
+            std::memcpy(hp + o_reg_out, out_beg.data(), sizeof(int64_t) * (p.n_regions + 1));
+            if (!long_pairs.empty()) std::memcpy(hp + o_long, long_pairs.data(), sizeof(LongPair) * long_pairs.size());
+            WarpJob* jd = (WarpJob*)(hp + o_jobs);
+            for (int k = 0; k < kSlots; k++)
+                if (!jobs_k[k].empty()) std::memcpy(jd + p.job_beg[k], jobs_k[k].data(), sizeof(WarpJob) * jobs_k[k].size());
+        });
     }
 
     uint8_t* dp = (uint8_t*)s.d_in.p;
@@ -648,14 +749,8 @@ int finalize_part(phmm_engine* e, DeviceCtx& dc, Slot& s, phmm_result* r, std::s
         }
         need_rescue += nr; marked += nm;
     };
-    const int nt = (int)std::min<int64_t>(e->host_threads, std::max<int64_t>(1, p.n_pairs / 65536));
-    if (nt <= 1) body(0, p.n_pairs);
-    else {
-        std::vector<std::thread> th;
-        for (int t = 0; t < nt; t++)
-            th.emplace_back(body, p.n_pairs * t / nt, p.n_pairs * (t + 1) / nt);
-        for (auto& x : th) x.join();
-    }
+    const int nt = (int)std::min<int64_t>(dc.pool->width(), std::max<int64_t>(1, p.n_pairs / 16384));
+    dc.pool->parallel_for(nt, [&](int t) { body(p.n_pairs * t / nt, p.n_pairs * (t + 1) / nt); });
     if (marked.load()) {
         // tier 3: pairs whose FP64 sum came out within reach of the denormal range are redone by the
         // flush-exact FP64 kernels now; they append to the same rescue list
@@ -842,6 +937,7 @@ int phmm_create(const phmm_options* opt, phmm_engine** out)
         std::unique_ptr<DeviceCtx> dc(new DeviceCtx());
         dc->ordinal = (opt && opt->devices) ? opt->devices[d] : d;
         if (dc->ordinal < 0 || dc->ordinal >= visible) return PHMM_ERR_NO_DEVICE;
+        dc->pool.reset(new HostPool(e->host_threads - 1));
         int rc = init_device(*dc, depth, err);
         if (rc) { fprintf(stderr, "phmm_create: %s\n", err.c_str()); return rc; }
         e->devs.push_back(std::move(dc));

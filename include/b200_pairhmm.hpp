@@ -51,7 +51,7 @@ public:
             opt.n_devices = devices.empty() ? 1 : (int32_t)devices.size();
             opt.devices = devices.empty() ? nullptr : devices.data();
             opt.pipeline_depth = 4;            // B200RegionBatcher keeps up to 3 batches in flight
-            opt.host_threads = 1;
+            opt.host_threads = 4;              // planning, packing and the log10 pass of a batch
             int rc = phmm_create(&opt, &eng);
             if (rc != PHMM_OK) throw std::runtime_error(std::string("phmm_create: ") + phmm_strerror(rc));
         }
