@@ -72,7 +72,15 @@ class _Result(C.Structure):
 EXPORTS = ["phmm_create", "phmm_destroy", "phmm_compute", "phmm_submit", "phmm_wait", "phmm_strerror",
            "phmm_last_error", "phmm_abi_version", "phmm_normalize_filter", "phmm_tables",
            "phmm_stage", "phmm_run_staged", "phmm_run_staged_ex", "phmm_run_staged_pipelined",
-           "phmm_fetch_staged", "phmm_free_staged"]
+           "phmm_fetch_staged", "phmm_free_staged", "phmm_plan"]
+
+class _PlanInfo(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("mode", C.c_int32), ("n_jobs", C.c_int32), ("n_long_pairs", C.c_int32),
+                ("haps_per_job", C.c_int32), ("hap_chunks", C.c_int32), ("haps_per_job64", C.c_int32),
+                ("hap_chunks64", C.c_int32), ("n_pairs", C.c_int64), ("n_cells", C.c_int64), ("n_shapes", C.c_int32),
+                ("shape_g", C.c_int32 * 32), ("shape_k", C.c_int32 * 32),
+                ("jobs_ragged", C.c_int32 * 32), ("jobs_aligned", C.c_int32 * 32)]
+
 
 _lib = None
 
@@ -101,6 +109,7 @@ def lib():
                                          C.POINTER(C.c_int32)]
         L.phmm_run_staged_pipelined.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int32,
                                                 C.POINTER(C.c_float), C.POINTER(C.c_int32)]
+        L.phmm_plan.argtypes = [C.POINTER(_Batch), C.c_int32, C.c_int32, C.POINTER(_PlanInfo), C.c_void_p, C.c_int64]
         L.phmm_fetch_staged.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_Result)]
         L.phmm_free_staged.argtypes = [C.c_void_p, C.c_void_p]; L.phmm_free_staged.restype = None
         _lib = L
@@ -157,12 +166,9 @@ class Batch:
 
     @property
     def n_cells(self):
-        rl = np.diff(self.read_off).astype(np.int64)
-        hl = np.diff(self.hap_off).astype(np.int64)
-        rsum = np.add.reduceat(rl, self.region_read_beg[:-1]) if self.n_reads else np.zeros(self.n_regions, np.int64)
-        hsum = np.add.reduceat(hl, self.region_hap_beg[:-1]) if self.n_haps else np.zeros(self.n_regions, np.int64)
-        rsum = np.where(self.reads_per_region > 0, rsum, 0)
-        hsum = np.where(self.haps_per_region > 0, hsum, 0)
+        # bases per region from the offset arrays (regions without reads or haplotypes contribute nothing)
+        rsum = np.diff(np.asarray(self.read_off, np.int64)[self.region_read_beg])
+        hsum = np.diff(np.asarray(self.hap_off, np.int64)[self.region_hap_beg])
         return int((rsum * hsum).sum())
 
     @property
@@ -226,6 +232,28 @@ class Batch:
         if explicit:
             kw.update(read_i=cat(ri), read_d=cat(rd_), read_c=cat(rc))
         return Batch(rrb, rhb, roff, cat(rb), cat(rq), hoff, cat(hb), **kw)
+
+
+def plan(batch, sm_count=148, host_threads=1):
+    """phmm_plan: the planner alone (no device).  Returns (info dict, jobs int32 array [n_jobs, 10])."""
+    info = _PlanInfo()
+    info.struct_size = C.sizeof(_PlanInfo)
+    cb = batch.c_struct()
+    rc = lib().phmm_plan(C.byref(cb), sm_count, host_threads, C.byref(info), None, 0)
+    if rc != PHMM_OK:
+        raise PhmmError(rc, lib().phmm_strerror(rc).decode())
+    jobs = np.zeros((info.n_jobs, 10), np.int32)
+    if info.n_jobs:
+        rc = lib().phmm_plan(C.byref(cb), sm_count, host_threads, C.byref(info), jobs.ctypes.data, info.n_jobs)
+        if rc != PHMM_OK:
+            raise PhmmError(rc, lib().phmm_strerror(rc).decode())
+    n = info.n_shapes
+    d = {k: getattr(info, k) for k in ("mode", "n_jobs", "n_long_pairs", "haps_per_job", "hap_chunks", "haps_per_job64",
+                                      "hap_chunks64", "n_pairs", "n_cells", "n_shapes")}
+    d["shapes"] = [(info.shape_g[i], info.shape_k[i]) for i in range(n)]
+    d["jobs_ragged"] = [info.jobs_ragged[i] for i in range(n)]
+    d["jobs_aligned"] = [info.jobs_aligned[i] for i in range(n)]
+    return d, jobs
 
 
 class Result:

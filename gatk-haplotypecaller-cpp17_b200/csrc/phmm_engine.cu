@@ -425,12 +425,21 @@ int launch_kernels(Slot& s, bool exact, int tier_lo, int tier_hi, std::string& e
 }
 
 // Pack regions [g0,g1) of the batch into the slot's pinned block, upload, launch, start D2H.
-int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1, int64_t out0,
-                     bool exact, bool do_launch, std::string& err)
+constexpr int kSlots = 2 * kNumShapes;      // kernel slot = shape + kNumShapes * aligned
+
+// What planning hands to packing: the job lists per kernel slot, the long-read pairs, the output offsets.
+struct Plan {
+    std::vector<int64_t> out_beg;            // first output index of every region within the part
+    std::vector<LongPair> long_pairs;
+    std::vector<WarpJob> jobs_k[kSlots];
+};
+
+// Pure host logic, no CUDA call: fills `p` (counts, mode, job ranges per slot, chunking) and `plan` for
+// regions [g0, g1) of the batch.  Exported for tests and diagnostics as phmm_plan().
+int plan_part(const phmm_batch* b, int g0, int g1, int64_t out0, int sm_count, float last_rescue_frac,
+              HostPool& pool, Part& p, Plan& plan, std::string& err)
 {
-    static const bool trace = getenv("PHMM_TRACE") != nullptr;      // development aid: host time per phase
-    const auto t_begin = std::chrono::steady_clock::now();
-    Part& p = s.part;
+    (void)err;
     p = Part();
     p.g0 = g0; p.g1 = g1; p.out0 = out0;
     p.n_regions = g1 - g0;
@@ -441,7 +450,7 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
     if (p.n_pairs == 0) return PHMM_OK;
     const int rb0 = b->read_off[r0], rb1 = b->read_off[r1];
     const int hb0 = b->hap_off[h0], hb1 = b->hap_off[h1];
-    const size_t read_bytes = (size_t)(rb1 - rb0), hap_bytes = (size_t)(hb1 - hb0);
+    const size_t hap_bytes = (size_t)(hb1 - hb0);
 
     // Batch-constant gap penalties?  Always, for the reference's own callers (sam/sam.hpp:30-32);
     // per-base arrays are scanned once here, and the general kernels run only if they really vary.
@@ -463,13 +472,13 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
     //      reads of a job within a few bases of each other (few dummy rows) and leaves one partial job per
     //      region instead of one per shape: on the reference's windows, where half of the reads are
     //      clipped to 10..149 bases, that is ~14% fewer jobs than grouping by each read's own shape. ----
-    constexpr int kSlots = 2 * kNumShapes;
     auto is_aligned = [&](int R, int sh) {
         return !general && (R % kShapes[sh].K == 0) && (kShapes[sh].K * kShapes[sh].G - R >= kShapes[sh].K);
     };
     struct PlannedJob { WarpJob job; int shape; bool aligned; };
     // first output index of every region within this part (also uploaded: region_out_beg)
-    std::vector<int64_t> out_beg(p.n_regions + 1, 0);
+    std::vector<int64_t>& out_beg = plan.out_beg;
+    out_beg.assign(p.n_regions + 1, 0);
     for (int g = g0; g < g1; g++)
         out_beg[g - g0 + 1] = out_beg[g - g0] + (int64_t)(b->region_read_beg[g + 1] - b->region_read_beg[g]) *
                                                     (b->region_hap_beg[g + 1] - b->region_hap_beg[g]);
@@ -480,7 +489,6 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
         int max_nh = 0;
         int64_t n_jobs_sh[kNumShapes] = {0}, n_aligned_sh[kNumShapes] = {0};
     };
-    HostPool& pool = *dc.pool;
     const int n_pieces = std::max(1, std::min(pool.width(), p.n_reads / 4096));
     std::vector<PlanPiece> pieces(n_pieces);
     std::vector<int> piece_cut(n_pieces + 1, g1);
@@ -531,7 +539,8 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
             }
         }
     });
-    std::vector<LongPair> long_pairs;
+    std::vector<LongPair>& long_pairs = plan.long_pairs;
+    long_pairs.clear();
     int64_t n_jobs_sh[kNumShapes] = {0}, n_aligned_sh[kNumShapes] = {0};
     size_t n_planned = 0;
     for (const PlanPiece& pc : pieces) {
@@ -543,7 +552,8 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
     }
     // Jobs whose reads are all a whole number of lanes take the ALIGNED kernels -- provided enough jobs of
     // that shape do (otherwise the split only adds small launches).
-    std::vector<WarpJob> jobs_k[kSlots];
+    std::vector<WarpJob>* jobs_k = plan.jobs_k;
+    for (int k = 0; k < kSlots; k++) jobs_k[k].clear();
     for (const PlanPiece& pc : pieces)
         for (const PlannedJob& pj : pc.planned) {
             const bool use_al = pj.aligned && n_aligned_sh[pj.shape] * 10 >= n_jobs_sh[pj.shape] && n_aligned_sh[pj.shape] >= 32;
@@ -569,7 +579,7 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
                 jobs_with_nh[b->region_hap_beg[g + 1] - b->region_hap_beg[g]]++;
             }
         const double h_mean = p.n_haps ? (double)hap_bytes / p.n_haps : 1.0;
-        const double resident = (double)dc.sm_count * 12;
+        const double resident = (double)sm_count * 12;
         constexpr double kChunkOverheadSteps = 128;   // calibrated on S3: 4 haplotypes per chunk beat 2 by 1%
         static const int force_hpj = [] { const char* s = getenv("PHMM_FORCE_HPJ"); return s ? atoi(s) : 0; }();
         int best_hpj = 1; double best_t = 0;
@@ -588,11 +598,37 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
         // of the whole launch -- so the redo cuts the haplotypes one per warp (warps without work exit on a
         // flag byte).  When most pairs are redone (long reads with low-quality tails) the coarse chunks
         // amortise setup and fill better; the choice follows the device's previous batch.
-        const bool dense = dc.last_rescue_frac > 0.05f;
+        const bool dense = last_rescue_frac > 0.05f;
         p.haps_per_job64 = dense ? hpj : 1;
         p.hap_chunks64 = (nhm + p.haps_per_job64 - 1) / p.haps_per_job64;
     }
 
+    return PHMM_OK;
+}
+
+int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1, int64_t out0,
+                     bool exact, bool do_launch, std::string& err)
+{
+    static const bool trace = getenv("PHMM_TRACE") != nullptr;      // development aid: host time per phase
+    const auto t_begin = std::chrono::steady_clock::now();
+    Part& p = s.part;
+    Plan plan;
+    HostPool& pool = *dc.pool;
+    {
+        int rcp = plan_part(b, g0, g1, out0, dc.sm_count, dc.last_rescue_frac, pool, p, plan, err);
+        if (rcp) return rcp;
+    }
+    if (p.n_pairs == 0) return PHMM_OK;
+    const int r0 = b->region_read_beg[g0], r1 = b->region_read_beg[g1];
+    const int h0 = b->region_hap_beg[g0], h1 = b->region_hap_beg[g1];
+    const int rb0 = b->read_off[r0], rb1 = b->read_off[r1];
+    const int hb0 = b->hap_off[h0], hb1 = b->hap_off[h1];
+    const size_t read_bytes = (size_t)(rb1 - rb0), hap_bytes = (size_t)(hb1 - hb0);
+    const bool general = p.mode == kModeGeneral;
+    const std::vector<int64_t>& out_beg = plan.out_beg;
+    const std::vector<LongPair>& long_pairs = plan.long_pairs;
+    const std::vector<WarpJob>* jobs_k = plan.jobs_k;
+    (void)r1; (void)h1; (void)rb1; (void)hb1;
     const auto t_planned = std::chrono::steady_clock::now();
     // ---- layout of the upload block ----
     size_t off = 0;
@@ -919,6 +955,43 @@ int phmm_normalize_filter(double* lik, int32_t n_reads, int32_t n_haps, const in
         kept += keep[i];
     }
     return kept;
+}
+
+int phmm_plan(const phmm_batch* b, int32_t sm_count, int32_t host_threads, phmm_plan_info* info,
+              int32_t* jobs_out, int64_t jobs_cap)
+{
+    if (!b || !info) return PHMM_ERR_INVALID_ARG;
+    std::string err;
+    int rc = validate_batch(b, err);
+    if (rc) return rc;
+    phmm_plan_info out{};
+    out.struct_size = (int32_t)sizeof(out);
+    out.n_shapes = kNumShapes;
+    for (int s = 0; s < kNumShapes; s++) { out.shape_g[s] = kShapes[s].G; out.shape_k[s] = kShapes[s].K; }
+    if (b->n_regions > 0) {
+        HostPool pool(std::max(1, host_threads) - 1);
+        Part p; Plan plan;
+        rc = plan_part(b, 0, b->n_regions, 0, sm_count > 0 ? sm_count : 148, 0.f, pool, p, plan, err);
+        if (rc) return rc;
+        out.mode = p.mode; out.n_jobs = p.n_jobs; out.n_long_pairs = (int32_t)plan.long_pairs.size();
+        out.haps_per_job = p.haps_per_job; out.hap_chunks = p.hap_chunks;
+        out.haps_per_job64 = p.haps_per_job64; out.hap_chunks64 = p.hap_chunks64;
+        out.n_pairs = p.n_pairs; out.n_cells = p.n_cells;
+        int64_t row = 0;
+        for (int k = 0; k < kSlots; k++) {
+            (k < kNumShapes ? out.jobs_ragged : out.jobs_aligned)[k % kNumShapes] = (int32_t)plan.jobs_k[k].size();
+            for (const WarpJob& j : plan.jobs_k[k]) {
+                if (jobs_out && row < jobs_cap) {
+                    int32_t* o = jobs_out + row * 10;
+                    o[0] = k; o[1] = j.region;
+                    for (int q = 0; q < kMaxJobReads; q++) o[2 + q] = j.read[q];
+                }
+                row++;
+            }
+        }
+    }
+    std::memcpy(info, &out, std::min<size_t>(sizeof(out), info->struct_size > 0 ? (size_t)info->struct_size : sizeof(out)));
+    return PHMM_OK;
 }
 
 int phmm_create(const phmm_options* opt, phmm_engine** out)

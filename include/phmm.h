@@ -139,6 +139,29 @@ int  phmm_tables(const float** ph2pr_f32, const float** mm_f32,
                  const double** ph2pr_f64, const double** mm_f64, int32_t* mm_entries);
 
 /*
+ * The planner on its own -- pure host logic, no device needed (tests, diagnostics): how a batch would be
+ * cut into warp jobs (reads of a region sorted by length, 2 per lane group, 32/G groups per warp, the
+ * job's lane-group shape (G lanes x K rows) taken from its longest read), which jobs take the lane-aligned
+ * kernels, how many haplotypes a (job, chunk) unit streams, and which reads go to the long-read kernel.
+ * jobs_out (optional): jobs_cap rows of 10 int32 {slot, region, read[8] (-1 = none)}, slot = shape index
+ * (+ n_shapes for a lane-aligned job), read indices within the batch.  info->struct_size must be set.
+ */
+#define PHMM_PLAN_MAX_SHAPES 32
+typedef struct phmm_plan_info {
+    int32_t struct_size;
+    int32_t mode;                     /* 0 per-base gap penalties, 1 batch-constant, 2 constant with i == d */
+    int32_t n_jobs, n_long_pairs;
+    int32_t haps_per_job, hap_chunks;       /* FP32 launches: haplotypes per unit, grid.y                */
+    int32_t haps_per_job64, hap_chunks64;   /* FP64 redo launches                                        */
+    int64_t n_pairs, n_cells;
+    int32_t n_shapes;
+    int32_t shape_g[PHMM_PLAN_MAX_SHAPES], shape_k[PHMM_PLAN_MAX_SHAPES];
+    int32_t jobs_ragged[PHMM_PLAN_MAX_SHAPES], jobs_aligned[PHMM_PLAN_MAX_SHAPES];
+} phmm_plan_info;
+int  phmm_plan(const phmm_batch* b, int32_t sm_count, int32_t host_threads, phmm_plan_info* info,
+               int32_t* jobs_out, int64_t jobs_cap);
+
+/*
  * Device-resident form, used by bench.py for the "inputs already in HBM" number:
  * phmm_stage uploads and plans once, phmm_run_staged launches the forward + rescue kernels
  * `iters` times back to back and returns the mean device time per iteration (CUDA events on the

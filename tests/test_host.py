@@ -93,3 +93,73 @@ def test_normalize_filter_semantics(pkg):
     assert lik[0].tolist() == [-1.0, -5.5, -5.5]
     assert keep.tolist() == [1, 0, 1]               # thresholds: -8, -8, -4 (best == threshold is kept)
     assert lik[1].tolist() == [-9.0, -13.0, -8.5]
+
+
+def _check_plan(pkg, b, host_threads=1):
+    """Invariants of the planner (phmm_plan, pure host logic): every read of at most 255 bases sits in
+    exactly one warp job of its own region, whose lane-group shape holds the job's longest read with a dummy
+    row to spare; lane-aligned jobs only hold lane-aligned reads; longer reads go to the long-read kernel,
+    one pair per haplotype of their region; cells and pairs are counted once."""
+    info, jobs = pkg.plan(b, host_threads=host_threads)
+    rl = np.diff(b.read_off)
+    region_of_read = np.repeat(np.arange(len(b.region_read_beg) - 1), np.diff(b.region_read_beg))
+    nh = np.diff(b.region_hap_beg)
+    assert info["n_pairs"] == b.n_pairs and info["n_cells"] == b.n_cells
+    assert info["n_jobs"] == len(jobs) == sum(info["jobs_ragged"]) + sum(info["jobs_aligned"])
+    seen = np.zeros(len(rl), np.int32)
+    n = info["n_shapes"]
+    for row in jobs:
+        slot, region, reads = int(row[0]), int(row[1]), [int(r) for r in row[2:] if r >= 0]
+        G, K = info["shapes"][slot % n]
+        assert 1 <= len(reads) <= 2 * (32 // G)
+        assert all(region_of_read[r] == region for r in reads)
+        assert max(rl[r] for r in reads) + 1 <= K * G                      # one dummy row on top is mandatory
+        if slot >= n:                                                      # lane-aligned job
+            assert info["mode"] != 0
+            assert all(rl[r] % K == 0 and K * G - rl[r] >= K for r in reads)
+        seen[reads] += 1
+    short = rl <= 255
+    has_haps = nh[region_of_read] > 0
+    assert np.array_equal(seen[short & has_haps], np.ones(int((short & has_haps).sum()), np.int32))
+    assert seen[~short].sum() == 0 and seen[~has_haps].sum() == 0
+    assert info["n_long_pairs"] == int(nh[region_of_read[~short]].sum())
+    assert 1 <= info["haps_per_job"] and info["haps_per_job"] * info["hap_chunks"] >= nh.max()
+    assert info["haps_per_job64"] * info["hap_chunks64"] >= nh.max()
+    return info, jobs
+
+
+def test_planner_invariants(pkg):
+    S = pkg.synth
+    _check_plan(pkg, S.random_small(11, n_regions=20, max_reads=40, max_haps=9, max_read_len=255, general_gaps=False))
+    info, _ = _check_plan(pkg, S.random_small(12, n_regions=6))                       # per-base gap penalties
+    assert info["mode"] == 0 and sum(info["jobs_aligned"]) == 0
+    info, jobs = _check_plan(pkg, S.s3(2))
+    assert info["mode"] == 2 and info["n_jobs"] == 2 * 64 and sum(info["jobs_aligned"]) == 128   # 150 = 15 lanes x 10 rows
+    b = next(S.s5_stream(128, windows_per_batch=128))
+    one, jobs1 = _check_plan(pkg, b, host_threads=1)
+    four, jobs4 = _check_plan(pkg, b, host_threads=4)
+    assert np.array_equal(jobs1, jobs4) and one == four                    # the plan does not depend on the thread count
+    # sorted packing: at most one partial job per region and shape class boundary -> close to reads / 4
+    n_reads = len(b.read_off) - 1
+    assert one["n_jobs"] <= n_reads / 4 + 2 * 128
+    # reads beyond 255 bases are planned for the long-read kernel
+    rng = np.random.default_rng(5)
+    alpha = np.frombuffer(b"ACGT", np.uint8)
+    mk = lambda n: alpha[rng.integers(0, 4, n)]
+    reads = [mk(300), mk(100), mk(2048), mk(255), mk(256)]
+    b = pkg.Batch.from_regions([(reads, [np.full(len(r), 60, np.uint8) for r in reads], [mk(500), mk(400), mk(30)]),
+                                ([mk(50)], [np.full(50, 60, np.uint8)], [])])
+    info, jobs = _check_plan(pkg, b)
+    assert info["n_long_pairs"] == 3 * 3 and info["n_jobs"] == 1
+
+
+def test_planner_chunks_follow_the_makespan_model(pkg):
+    """Many haplotypes per region and plenty of jobs -> several haplotypes per (job, chunk) unit; a ragged
+    stream with a few many-haplotype regions -> short units, so that no warp runs far longer than the rest."""
+    S = pkg.synth
+    info, _ = pkg.plan(S.s3(128))
+    assert info["haps_per_job"] == 4 and info["hap_chunks"] == 4 and info["haps_per_job64"] == 1
+    info, _ = pkg.plan(next(S.s5_stream(512, windows_per_batch=512)))
+    assert info["haps_per_job"] <= 3
+    info, _ = pkg.plan(S.s3(1))
+    assert info["haps_per_job"] == 1 and info["hap_chunks"] == 16          # few jobs: every haplotype its own unit
