@@ -215,6 +215,33 @@ def test_full_size_s3_properties(pkg, engine, oracle):
         assert _maxerr(got.log10[o:o + sub.n_pairs][resc], want["log10"][resc]) <= TOL64
 
 
+@pytest.mark.parametrize("name,make,spot", [
+    ("S2 full size: 256 regions of 64 reads (100) x 8 haplotypes (300)", lambda S: S.s2(256), (0, 100, 255)),
+    ("S4 full size: 16 regions of 128 reads (150-250, low-quality tails) x 16 haplotypes (600-1000)", lambda S: S.s4(16), (3, 12)),
+    ("S5: 1024 windows of the ragged active-region stream", lambda S: next(S.s5_stream(1024, windows_per_batch=1024)), (1, 500, 1023)),
+])
+def test_full_size_other_configs(pkg, engine, oracle, name, make, spot):
+    """BASELINE configs 2, 4 and 5 at full size: batch-split invariance (a region computed alone gives the
+    same bits as inside the big batch, whatever jobs / chunks / lane partners the planner gave it) and an
+    oracle check of whole regions."""
+    b = make(pkg.synth)
+    got = engine.compute(b)
+    assert got.stats["n_cells"] == b.n_cells and got.stats["n_pairs"] == b.n_pairs
+    if name.startswith("S4"):
+        assert got.rescued.all()
+    for g in spot:
+        sub = b.slice_regions(g, g + 1)
+        o = int(b.region_out_beg[g])
+        mine = got.log10[o:o + sub.n_pairs]
+        alone = engine.compute(sub)
+        assert np.array_equal(alone.log10.view(np.uint64), mine.view(np.uint64)), f"{name}: region {g} alone"
+        want = oracle.batch(sub, threads=16)
+        resc = want["rescued"].astype(bool)
+        assert np.array_equal(got.rescued[o:o + sub.n_pairs].astype(bool), resc)
+        assert _maxerr(mine[~resc], want["log10"][~resc]) <= TOL32
+        assert _maxerr(mine[resc], want["log10"][resc]) <= TOL64
+
+
 def test_call_surface_compute_likelihoods(pkg, engine, golden):
     """hc::IntelPairHMM::compute_likelihoods semantics (cap at best-4.5, poorly modelled reads erased)
     against the reference's own outputs (Appendix A.2 + six regions)."""
