@@ -81,7 +81,7 @@ inline int pick_shape_uncached(int R, int H)
 {
     static const int force = [] { const char* s = getenv("PHMM_FORCE_GROUP"); return s ? atoi(s) : 0; }();
     int best = -1; double best_cost = 0;
-    for (int s = 0; s < kNumShapes; s++) {
+    for (int s = 0; s < kFirstPackedShape; s++) {
         const int G = kShapes[s].G, K = kShapes[s].K;
         if (K * G < R + 1) continue;
         if (force && G != force) continue;
@@ -89,9 +89,27 @@ inline int pick_shape_uncached(int R, int H)
         if (best < 0 || cost < best_cost) { best = s; best_cost = cost; }
     }
     if (best < 0 && force)      // forced width cannot hold this read: fall back to any feasible shape
-        for (int s = 0; s < kNumShapes; s++)
+        for (int s = 0; s < kFirstPackedShape; s++)
             if (kShapes[s].K * kShapes[s].G >= R + 1) { best = s; break; }
     return best;
+}
+
+// PACKED shape (free-width lane groups, phmm_kernels.cuh) for reads of exactly R bases, or -1: R = K * nl for
+// a compiled K with groups of nl lanes that fill at least 90% of the warp (8, 10, 15 or 16 lanes), except
+// where a power-of-two group with one idle lane does as well (150 = 15 x 10 on 16 lanes: ALIGNED).
+inline int packed_shape(int R, int* lanes_per_group)
+{
+    static const bool off = getenv("PHMM_NO_PACKED") != nullptr;
+    if (off) return -1;
+    for (int s = kNumShapes - 1; s >= kFirstPackedShape; s--) {          // tallest lanes first
+        const int K = kShapes[s].K;
+        if (R % K) continue;
+        const int nl = R / K;
+        if (nl != 8 && nl != 10 && nl != 16 && !(nl == 15 && K != 10)) continue;
+        if (lanes_per_group) *lanes_per_group = nl;
+        return s;
+    }
+    return -1;
 }
 
 // ---- grow-only buffers (the memory pool) ----------------------------------------------------
@@ -498,6 +516,17 @@ int plan_part(const phmm_batch* b, int g0, int g1, int64_t out0, int sm_count, f
         while (g < g1 && b->region_read_beg[g] < want) g++;
         piece_cut[t] = g;
     }
+    // PACKED jobs hold reads of ONE length; worth a kernel of their own only when the batch has plenty
+    bool packed_on[kMaxReadLenCompiled + 1] = {false};
+    if (!general) {
+        std::vector<int32_t> n_of_len(kMaxReadLenCompiled + 1, 0);
+        for (int r = r0; r < r1; r++) {
+            const int R = b->read_off[r + 1] - b->read_off[r];
+            if (R <= kMaxReadLenCompiled) n_of_len[R]++;
+        }
+        for (int R = 1; R <= kMaxReadLenCompiled; R++)
+            packed_on[R] = n_of_len[R] >= 256 && n_of_len[R] * 10 >= p.n_reads && packed_shape(R, nullptr) >= 0;
+    }
     pool.parallel_for(n_pieces, [&](int t) {
         PlanPiece& pc = pieces[t];
         std::vector<std::pair<int, int>> by_len;         // (read length, read index within the part)
@@ -518,6 +547,27 @@ int plan_part(const phmm_batch* b, int g0, int g1, int64_t out0, int sm_count, f
                     continue;
                 }
                 by_len.emplace_back(R, r - r0);
+            }
+            // reads of a PACKED length: jobs of 2 reads per group, floor(32 / nl) groups per warp
+            for (size_t i = 0; i < by_len.size();) {
+                if (!packed_on[by_len[i].first]) { ++i; continue; }
+                const int R = by_len[i].first;
+                int nl = 0;
+                const int sh = packed_shape(R, &nl);
+                const int cap = 2 * std::min(32 / nl, kMaxJobReads / 2);
+                PlannedJob pj;
+                pj.shape = sh; pj.aligned = true;
+                pj.job.region = g - g0;
+                int q = 0;
+                size_t w = i;                                  // compact the rest of by_len over the reads taken
+                for (size_t j = i; j < by_len.size(); j++) {
+                    if (by_len[j].first == R && q < cap) pj.job.read[q++] = by_len[j].second;
+                    else by_len[w++] = by_len[j];
+                }
+                by_len.resize(w);
+                for (; q < kMaxJobReads; q++) pj.job.read[q] = -1;
+                pc.n_jobs_sh[sh]++; pc.n_aligned_sh[sh]++;
+                pc.planned.push_back(pj);
             }
             std::sort(by_len.begin(), by_len.end(), [](const std::pair<int, int>& x, const std::pair<int, int>& y) {
                 return x.first != y.first ? x.first > y.first : x.second < y.second;
@@ -556,7 +606,8 @@ int plan_part(const phmm_batch* b, int g0, int g1, int64_t out0, int sm_count, f
     for (int k = 0; k < kSlots; k++) jobs_k[k].clear();
     for (const PlanPiece& pc : pieces)
         for (const PlannedJob& pj : pc.planned) {
-            const bool use_al = pj.aligned && n_aligned_sh[pj.shape] * 10 >= n_jobs_sh[pj.shape] && n_aligned_sh[pj.shape] >= 32;
+            const bool use_al = pj.shape >= kFirstPackedShape ||        // PACKED shapes only exist as aligned kernels
+                                (pj.aligned && n_aligned_sh[pj.shape] * 10 >= n_jobs_sh[pj.shape] && n_aligned_sh[pj.shape] >= 32);
             jobs_k[pj.shape + (use_al ? kNumShapes : 0)].push_back(pj.job);
         }
     (void)n_planned;

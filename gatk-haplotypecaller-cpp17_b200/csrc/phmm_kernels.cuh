@@ -255,12 +255,21 @@ enum : int { kModeGeneral = 0, kModeConst = 1, kModeConstShared = 2 };
 // dummy rows fill whole lanes.  Then no row needs its own Y self-transition: all rows use the uniform
 // factor (one register-file read less per cell, K register pairs less per lane), dummy lanes may
 // compute garbage Y, and the only Y that matters -- the one handed to the first real lane -- is
-// overridden with init_Y as it is shuffled out.  Standard read lengths (100, 150, 250) qualify.
-template <class P, int K, int G, int MODE, bool EXACT, bool ALIGNED>
+// overridden with init_Y as it is shuffled out.  Standard read lengths (150 = 15 lanes x 10 rows) qualify.
+//
+// PACKED (with ALIGNED, G == 32): lane groups of ANY width.  Every read of the job has the same length
+// R = K * nl; the warp holds floor(32 / nl) groups of nl consecutive lanes back to back (100 bases: three
+// groups of 10 lanes, 30 of 32 lanes busy, where the power-of-two groups manage 100 of 112 slots with a
+// private Y factor per row).  No dummy rows or lanes at all: the first lane of a group takes the
+// reference's row 0 -- (0, 0, init_Y) -- instead of what the shuffle hands it from the group above:
+// zeroed factors annihilate the M and X it received, a select replaces the Y.  Lanes behind the last
+// group shadow group 0 with zero priors and never emit.
+template <class P, int K, int G, int MODE, bool EXACT, bool ALIGNED, bool PACKED = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, (P::kIsF32 && K <= 5 && MODE != kModeGeneral) ? PHMM_MIN_WARPS / kWarpsPerCta : 1)
 forward_kernel(const KernelArgs args)
 {
     static_assert(!ALIGNED || MODE != kModeGeneral, "ALIGNED needs batch-constant gap penalties");
+    static_assert(!PACKED || (ALIGNED && G == 32), "PACKED is a variant of ALIGNED on the whole warp");
     using S = typename P::S;
     using V = typename P::V;
     constexpr int NH = P::NH;
@@ -278,8 +287,8 @@ forward_kernel(const KernelArgs args)
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int grp  = lane / G;
-    const int l    = lane % G;
+    int grp = lane / G;                   // lane group and lane within it (PACKED: set once the job is known)
+    int l   = lane % G;
     const int job_idx = blockIdx.x * kWarpsPerCta + warp;
     if (job_idx >= args.n_jobs) return;
 
@@ -300,6 +309,15 @@ forward_kernel(const KernelArgs args)
     const int h_last  = min(nh, h_first + args.haps_per_job);
     const int rd_beg  = args.region_read_beg[job.region];
     const int64_t out_base = args.region_out_beg[job.region];
+    int nl = G;                           // lanes per group
+    bool lane_live = true;                // PACKED: false behind the last group
+    if (PACKED) {
+        nl = (args.read_off[job.read[0] + 1] - args.read_off[job.read[0]]) / K;    // same for every read of the job
+        const int n_grp = min(32 / nl, kMaxJobReads / 2);
+        grp = lane / nl; l = lane - grp * nl;
+        lane_live = grp < n_grp;
+        if (!lane_live) { l = min(lane - n_grp * nl, nl - 1); grp = 0; }
+    }
 
     const S* __restrict__ ph2pr = P::ph2pr(args);
     const S* __restrict__ mmtab = P::mm(args);
@@ -311,7 +329,7 @@ forward_kernel(const KernelArgs args)
     int* s_hidx   = reinterpret_cast<int*>(s_inity + args.haps_per_job);
     int* s_apos   = s_hidx + args.haps_per_job;
     int* s_alen   = s_apos + args.haps_per_job;
-    V* const my_tab = reinterpret_cast<V*>(stab + grp * 5 * SUBT + l * LANE_B);   // + b * SUBT, [k]
+    V* const my_tab = reinterpret_cast<V*>(stab + (PACKED ? 0 : grp) * 5 * SUBT + (PACKED ? lane : l) * LANE_B);   // + b * SUBT, [k]
 
     constexpr int NSUB = 2 / NH;         // FP64: the two reads of a group one after the other
 #pragma unroll 1
@@ -321,13 +339,13 @@ forward_kernel(const KernelArgs args)
 #pragma unroll
         for (int hf = 0; hf < NH; ++hf) {
             rd[hf] = job.read[2 * grp + sub * NH + hf];
-            valid[hf] = rd[hf] >= 0;
+            valid[hf] = rd[hf] >= 0 && lane_live;
         }
         if (!P::kIsF32) {
             // rescue kernel: skip this read unless some haplotype of the chunk needs the redo
             bool need = false;
             if (valid[0])
-                for (int h = h_first + l; h < h_last; h += G)
+                for (int h = h_first + l; h < h_last; h += nl)
                     need |= needs_redo(args.raw32[out_base + (int64_t)(rd[0] - rd_beg) * nh + h]);
             if (!__any_sync(0xffffffffu, need)) continue;
         }
@@ -355,14 +373,14 @@ forward_kernel(const KernelArgs args)
                 const int r  = rd[hf];
                 const int ro = args.read_off[r];
                 const int R  = args.read_off[r + 1] - ro;
-                pad[hf] = K * G - R;      // >= 1 by construction of the plan
+                pad[hf] = PACKED ? 0 : K * G - R;      // >= 1 by construction of the plan (PACKED: R == K * nl)
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
                     const int ri = l * K + k - pad[hf];
                     S mat = 0, mis = 0, yy = P::one();
                     S mm_ = 0, gapm = 0, mx_ = 0, my_ = 0;
                     int rc = 4;
-                    if (ri >= 0) {
+                    if (ri >= 0 && (!PACKED || lane_live)) {
                         rc = base_code(args.read_bases[ro + ri]);
                         const S dist = ph2pr[args.read_q[ro + ri] & 127];
                         mat = P::ssub(P::one(), dist);
@@ -398,8 +416,13 @@ forward_kernel(const KernelArgs args)
         }
         // row 0 of the lane takes its "cell above" from the shuffle; lane 0 receives its own
         // bottom row back (shfl_up at the group edge), which these two zeros annihilate.
-        const V pMX0 = (l == 0) ? P::splat(0) : pMX[0];
-        const V pXX0 = (l == 0) ? P::splat(0) : (CONSTG ? pXXc : pYY[0]);
+        // PACKED: the first lane of EVERY group stands under the reference's row 0, whatever the lane above
+        // (the last lane of another read's group) shuffles down: two more zeroed factors for the diagonal.
+        const bool top = (l == 0);
+        const V pMX0 = top ? P::splat(0) : pMX[0];
+        const V pXX0 = top ? P::splat(0) : (CONSTG ? pXXc : pYY[0]);
+        const V pMM0   = (PACKED && top) ? P::splat(0) : pMM[0];
+        const V pGAPX0 = (PACKED && top) ? P::splat(0) : pGAPM[0];
         bool dummy_lane[NH];              // ALIGNED: this lane holds only dummy rows of packed read hf
 #pragma unroll
         for (int hf = 0; hf < NH; ++hf) dummy_lane[hf] = l * K < pad[hf];
@@ -462,6 +485,7 @@ forward_kernel(const KernelArgs args)
         // previous column (dg*).  Lane 0 never uses them (its row 0 is a dummy row with zero
         // priors, pMX0 = pXX0 = 0 and pYY = 1).
         V inM = P::splat(0), inX = P::splat(0), inY = P::shfl_up(Y[K - 1], G);
+        if (PACKED) inY = top ? P::splat(inity_cur) : P::splat(0);
         V dgM = inM, dgX = inX, dgY = inY;
         V qM = inM, qX = inX, qY = inY;   // kSkew == 2: bottom row in flight (sent last step, used next step)
 
@@ -485,11 +509,13 @@ forward_kernel(const KernelArgs args)
                 const V dM = k ? M[k - 1] : dgM;            // (row-1, c-1)
                 const V dX = k ? X[k - 1] : dgX;
                 const V dY = k ? Y[k - 1] : dgY;
+                const V cMM = (PACKED && k == 0) ? pMM0 : pMM[kk];
+                const V cGX = (PACKED && k == 0) ? pGAPX0 : pGAPM[kk];
                 if (EXACT) {
                     // reference operation order, unfused (avx-pairhmm-template.h:188)
-                    t0[k] = P::addx(P::addx(MUL(dM, pMM[kk]), MUL(dX, pGAPM[kk])), MUL(dY, pGAPM[kk]));
+                    t0[k] = P::addx(P::addx(MUL(dM, cMM), MUL(dX, cGX)), MUL(dY, pGAPM[kk]));
                 } else {
-                    t0[k] = P::fma(dY, pGAPM[kk], P::fma(dX, pGAPM[kk], MUL(dM, pMM[kk])));
+                    t0[k] = P::fma(dY, pGAPM[kk], P::fma(dX, cGX, MUL(dM, cMM)));
                 }
             }
             // Y from the left neighbour (:197); needs M of the previous column
@@ -525,21 +551,21 @@ forward_kernel(const KernelArgs args)
         auto rotate = [&]() {
             dgM = inM; dgX = inX; dgY = inY;
             // ALIGNED: a dummy lane's Y is garbage; what the lane below must see is row 0's init_Y
-            const V outY = ALIGNED ? P::sel(dummy_lane[0], dummy_lane[NH - 1], P::splat(inity_cur), Y[K - 1]) : Y[K - 1];
+            // PACKED: the lane above a group's first lane belongs to another read and runs nl-1 columns
+            // behind, so the RECEIVER substitutes its own haplotype's init_Y
+            const V outY = (ALIGNED && !PACKED) ? P::sel(dummy_lane[0], dummy_lane[NH - 1], P::splat(inity_cur), Y[K - 1]) : Y[K - 1];
+            V rM = P::shfl_up(M[K - 1], G), rX = P::shfl_up(X[K - 1], G), rY = P::shfl_up(outY, G);
+            if (PACKED) rY = P::sel(top, top, P::splat(inity_cur), rY);
             if (kSkew == 2) {
                 inM = qM; inX = qX; inY = qY;
-                qM = P::shfl_up(M[K - 1], G);
-                qX = P::shfl_up(X[K - 1], G);
-                qY = P::shfl_up(outY, G);
+                qM = rM; qX = rX; qY = rY;
             } else {
-                inM = P::shfl_up(M[K - 1], G);
-                inX = P::shfl_up(X[K - 1], G);
-                inY = P::shfl_up(outY, G);
+                inM = rM; inX = rX; inY = rY;
             }
         };
         // a haplotype ends for this lane
         auto boundary = [&]() {
-            if (l == G - 1) {
+            if (l == nl - 1) {
                 const int h = s_hidx[jcur];
 #pragma unroll
                 for (int hf = 0; hf < NH; ++hf) {
@@ -565,17 +591,19 @@ forward_kernel(const KernelArgs args)
             ++jcur;
             inity_cur = s_inity[min(jcur, n - 1)];
             reset_state(inity_cur);
+            // PACKED: a group's first lane enters the next haplotype -- row 0 above it changes with it
+            if (PACKED && top) { inY = P::splat(inity_cur); if (kSkew == 2) qY = inY; }
         };
 
         // shared address of this lane's byte at step t is bp + t
-        const uint32_t bp = (uint32_t)__cvta_generic_to_shared(sb) + (uint32_t)(kSkew * (G - 1 - l));
+        const uint32_t bp = (uint32_t)__cvta_generic_to_shared(sb) + (uint32_t)(kSkew * (nl - 1 - l));
         int t = 0;
         uint32_t b_next = lds_u8(bp);
 #pragma unroll 1
         for (int j = 0; j <= n; ++j) {
             // [t_a, t_s): every lane of the group is inside haplotype j -> no tests at all
             const int t_a = (j < n) ? s_apos[j] : p_end + 1;
-            const int t_s = (j < n) ? t_a + s_alen[j] - kSkew * (G - 1) : t_a;
+            const int t_s = (j < n) ? t_a + s_alen[j] - kSkew * (nl - 1) : t_a;
             // lanes straddle two haplotypes (or the ends of the stream)
 #pragma unroll 1
             for (; t < t_a; ++t) {

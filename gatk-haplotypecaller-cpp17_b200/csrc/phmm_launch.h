@@ -12,10 +12,14 @@ struct Shape { int G, K; };
 
 // Shapes compiled in this round.  Wide groups (G=32) keep registers low; narrow groups (G=16) put
 // more rows in a lane: fewer fill/drain steps and more FP32 work per shuffle/loop instruction.
-constexpr int kNumShapes = 18;
+// The last three are the PACKED shapes (free-width lane groups on the whole warp, phmm_kernels.cuh): they
+// only exist as "aligned" kernels of the constant-gap modes and are never picked by read length alone.
+constexpr int kNumShapes = 21;
+constexpr int kFirstPackedShape = 18;
 constexpr Shape kShapes[kNumShapes] = {
     {32, 1}, {32, 2}, {32, 3}, {32, 4}, {32, 5}, {32, 6}, {32, 7}, {32, 8},
-    {16, 1}, {16, 2}, {16, 3}, {16, 4}, {16, 5}, {16, 6}, {16, 7}, {16, 8}, {16, 9}, {16, 10}};
+    {16, 1}, {16, 2}, {16, 3}, {16, 4}, {16, 5}, {16, 6}, {16, 7}, {16, 8}, {16, 9}, {16, 10},
+    {32, 8}, {32, 9}, {32, 10}};
 constexpr int kMaxReadLenCompiled = 32 * 8 - 1;   // 255
 
 // Reads longer than kMaxReadLenCompiled take the one-warp-per-pair kernel of phmm_long.cu.
@@ -37,6 +41,15 @@ void register_f64_exact(KernelTab& tab);
 
 #define PHMM_REGISTER_ALL(POLICY, EXACT)                                                         \
     do {                                                                                         \
+        for (int m_ = 0; m_ < kNumModes; m_++)                                                   \
+            for (int a_ = 0; a_ < 2; a_++)                                                       \
+                for (int s_ = kFirstPackedShape; s_ < kNumShapes; s_++) tab[m_][a_][s_] = nullptr; \
+        tab[1][1][18] = forward_kernel<POLICY, 8, 32, 1, EXACT, true, true>;                     \
+        tab[1][1][19] = forward_kernel<POLICY, 9, 32, 1, EXACT, true, true>;                     \
+        tab[1][1][20] = forward_kernel<POLICY, 10, 32, 1, EXACT, true, true>;                    \
+        tab[2][1][18] = forward_kernel<POLICY, 8, 32, 2, EXACT, true, true>;                     \
+        tab[2][1][19] = forward_kernel<POLICY, 9, 32, 2, EXACT, true, true>;                     \
+        tab[2][1][20] = forward_kernel<POLICY, 10, 32, 2, EXACT, true, true>;                    \
         tab[0][0][0] = forward_kernel<POLICY, 1, 32, 0, EXACT, false>;                           \
         tab[0][0][1] = forward_kernel<POLICY, 2, 32, 0, EXACT, false>;                           \
         tab[0][0][2] = forward_kernel<POLICY, 3, 32, 0, EXACT, false>;                           \
