@@ -231,8 +231,10 @@ struct Slot {
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
     cudaEvent_t ev_k32 = nullptr;            // after the FP32 launch of a single-shape batch (dominant-kernel timing)
     bool k32_valid = false;
-    PinnedBuf h_in, h_out, h_rescue;
-    DeviceBuf d_in, d_out, d_rescue, d_flags;
+    PinnedBuf h_in, h_jobs, h_out, h_rescue;
+    DeviceBuf d_in, d_jobs, d_out, d_rescue, d_flags;
+    int async_rc = PHMM_OK;                  // failure after the submitter was released: reported by phmm_wait
+    std::string async_err;
     bool busy = false;
     Part part;
     KernelArgs args{};
@@ -445,6 +447,23 @@ int launch_kernels(Slot& s, bool exact, int tier_lo, int tier_hi, std::string& e
 // Pack regions [g0,g1) of the batch into the slot's pinned block, upload, launch, start D2H.
 constexpr int kSlots = 2 * kNumShapes;      // kernel slot = shape + kNumShapes * aligned
 
+// Batch-constant gap penalties?  Always, for the reference's own callers (sam/sam.hpp:30-32); per-base
+// arrays are scanned once, and the general kernels run only if they really vary over bytes [rb0, rb1).
+int detect_gap_mode(const phmm_batch* b, int rb0, int rb1, uint8_t gap[3])
+{
+    bool constant = true;
+    if (!b->read_i) {
+        gap[0] = b->gap_open_i; gap[1] = b->gap_open_d; gap[2] = b->gap_cont_c;
+    } else {
+        gap[0] = b->read_i[rb0]; gap[1] = b->read_d[rb0]; gap[2] = b->read_c[rb0];
+        const uint8_t* end;
+        end = b->read_i + rb1; for (const uint8_t* q = b->read_i + rb0; q < end && constant; ++q) constant = (*q == gap[0]);
+        end = b->read_d + rb1; for (const uint8_t* q = b->read_d + rb0; q < end && constant; ++q) constant = (*q == gap[1]);
+        end = b->read_c + rb1; for (const uint8_t* q = b->read_c + rb0; q < end && constant; ++q) constant = (*q == gap[2]);
+    }
+    return !constant ? kModeGeneral : (((gap[0] & 127) == (gap[1] & 127)) ? kModeConstShared : kModeConst);
+}
+
 // What planning hands to packing: the job lists per kernel slot, the long-read pairs, the output offsets.
 struct Plan {
     std::vector<int64_t> out_beg;            // first output index of every region within the part
@@ -472,17 +491,7 @@ int plan_part(const phmm_batch* b, int g0, int g1, int64_t out0, int sm_count, f
 
     // Batch-constant gap penalties?  Always, for the reference's own callers (sam/sam.hpp:30-32);
     // per-base arrays are scanned once here, and the general kernels run only if they really vary.
-    bool constant = true;
-    if (!b->read_i) {
-        p.gap[0] = b->gap_open_i; p.gap[1] = b->gap_open_d; p.gap[2] = b->gap_cont_c;
-    } else {
-        p.gap[0] = b->read_i[rb0]; p.gap[1] = b->read_d[rb0]; p.gap[2] = b->read_c[rb0];
-        const uint8_t* end;
-        end = b->read_i + rb1; for (const uint8_t* q = b->read_i + rb0; q < end && constant; ++q) constant = (*q == p.gap[0]);
-        end = b->read_d + rb1; for (const uint8_t* q = b->read_d + rb0; q < end && constant; ++q) constant = (*q == p.gap[1]);
-        end = b->read_c + rb1; for (const uint8_t* q = b->read_c + rb0; q < end && constant; ++q) constant = (*q == p.gap[2]);
-    }
-    p.mode = !constant ? kModeGeneral : (((p.gap[0] & 127) == (p.gap[1] & 127)) ? kModeConstShared : kModeConst);
+    p.mode = detect_gap_mode(b, rb0, rb1, p.gap);
     const bool general = p.mode == kModeGeneral;
 
     // ---- plan: per region, reads sorted by length and cut into warp jobs (2 reads per lane group, 32/G
@@ -657,57 +666,51 @@ int plan_part(const phmm_batch* b, int g0, int g1, int64_t out0, int sm_count, f
     return PHMM_OK;
 }
 
+// Regions [g0,g1) of the batch on one device, in two phases.
+//   A (reads the caller's arrays): pack them into the slot's pinned block -- offsets rebased to the part --
+//     and start its upload; then `copied()` releases the submitter, who may free or reuse its arrays.
+//   B (reads only the packed copy): plan (plan_part on a view of the pinned block), upload the job list,
+//     launch, start the download.  Runs while the submitter validates and packs its next batch and while the
+//     data upload is in flight; a failure here is kept in the slot and reported by phmm_wait.
 int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1, int64_t out0,
-                     bool exact, bool do_launch, std::string& err)
+                     bool exact, bool do_launch, std::string& err, const std::function<void()>& copied = {})
 {
     static const bool trace = getenv("PHMM_TRACE") != nullptr;      // development aid: host time per phase
     const auto t_begin = std::chrono::steady_clock::now();
     Part& p = s.part;
-    Plan plan;
+    p = Part();
+    p.g0 = g0; p.g1 = g1; p.out0 = out0;
+    p.n_regions = g1 - g0;
     HostPool& pool = *dc.pool;
-    {
-        int rcp = plan_part(b, g0, g1, out0, dc.sm_count, dc.last_rescue_frac, pool, p, plan, err);
-        if (rcp) return rcp;
-    }
-    if (p.n_pairs == 0) return PHMM_OK;
     const int r0 = b->region_read_beg[g0], r1 = b->region_read_beg[g1];
     const int h0 = b->region_hap_beg[g0], h1 = b->region_hap_beg[g1];
+    const int n_reads = r1 - r0, n_haps = h1 - h0, n_regions = g1 - g0;
+    p.n_reads = n_reads; p.n_haps = n_haps;
+    p.n_pairs = batch_pairs(b, g0, g1);
+    if (p.n_pairs == 0) { if (copied) copied(); return PHMM_OK; }
     const int rb0 = b->read_off[r0], rb1 = b->read_off[r1];
     const int hb0 = b->hap_off[h0], hb1 = b->hap_off[h1];
     const size_t read_bytes = (size_t)(rb1 - rb0), hap_bytes = (size_t)(hb1 - hb0);
-    const bool general = p.mode == kModeGeneral;
-    const std::vector<int64_t>& out_beg = plan.out_beg;
-    const std::vector<LongPair>& long_pairs = plan.long_pairs;
-    const std::vector<WarpJob>* jobs_k = plan.jobs_k;
-    (void)r1; (void)h1; (void)rb1; (void)hb1;
-    const auto t_planned = std::chrono::steady_clock::now();
-    // ---- layout of the upload block ----
+    uint8_t gap[3];
+    const bool general = detect_gap_mode(b, rb0, rb1, gap) == kModeGeneral;
+
+    // ---- phase A: layout of the data block, pack, upload ----
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
-    const size_t o_read_off = take(sizeof(int32_t) * (p.n_reads + 1));
-    const size_t o_hap_off  = take(sizeof(int32_t) * (p.n_haps + 1));
-    const size_t o_reg_read = take(sizeof(int32_t) * (p.n_regions + 1));
-    const size_t o_reg_hap  = take(sizeof(int32_t) * (p.n_regions + 1));
-    const size_t o_reg_out  = take(sizeof(int64_t) * (p.n_regions + 1));
+    const size_t o_read_off = take(sizeof(int32_t) * (n_reads + 1));
+    const size_t o_hap_off  = take(sizeof(int32_t) * (n_haps + 1));
+    const size_t o_reg_read = take(sizeof(int32_t) * (n_regions + 1));
+    const size_t o_reg_hap  = take(sizeof(int32_t) * (n_regions + 1));
+    const size_t o_reg_out  = take(sizeof(int64_t) * (n_regions + 1));
     const size_t o_bases    = take(read_bytes);
     const size_t o_q        = take(read_bytes);
     const size_t o_gi       = general ? take(read_bytes) : 0;
     const size_t o_gd       = general ? take(read_bytes) : 0;
     const size_t o_gc       = general ? take(read_bytes) : 0;
     const size_t o_haps     = take(hap_bytes);
-    const size_t o_jobs     = take(sizeof(WarpJob) * p.n_jobs);
-    p.n_long = (int)long_pairs.size();
-    const size_t o_long     = take(sizeof(LongPair) * long_pairs.size());
     const size_t in_bytes   = off;
-
     CUDA_TRY(s.h_in.reserve(in_bytes));
     CUDA_TRY(s.d_in.reserve(in_bytes));
-    const size_t out_bytes = 16 + sizeof(float) * (size_t)p.n_pairs;
-    CUDA_TRY(s.h_out.reserve(out_bytes));
-    CUDA_TRY(s.d_out.reserve(out_bytes));
-    CUDA_TRY(s.d_rescue.reserve(sizeof(RescueOut) * (size_t)p.n_pairs));
-    CUDA_TRY(s.d_flags.reserve((size_t)p.n_jobs * p.hap_chunks + 16));
-
     uint8_t* hp = (uint8_t*)s.h_in.p;
     {
         // the byte arrays are cut into one slice per host thread; the small index arrays ride along
@@ -729,21 +732,67 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
                 return;
             }
             int32_t* ro = (int32_t*)(hp + o_read_off);
-            for (int r = 0; r <= p.n_reads; r++) ro[r] = b->read_off[r0 + r] - rb0;
+            for (int r = 0; r <= n_reads; r++) ro[r] = b->read_off[r0 + r] - rb0;
             int32_t* ho = (int32_t*)(hp + o_hap_off);
-            for (int h = 0; h <= p.n_haps; h++) ho[h] = b->hap_off[h0 + h] - hb0;
+            for (int h = 0; h <= n_haps; h++) ho[h] = b->hap_off[h0 + h] - hb0;
             int32_t* rr = (int32_t*)(hp + o_reg_read);
             int32_t* rh = (int32_t*)(hp + o_reg_hap);
-            for (int g = 0; g <= p.n_regions; g++) {
+            int64_t* rout = (int64_t*)(hp + o_reg_out);
+            int64_t acc = 0;
+            for (int g = 0; g <= n_regions; g++) {
                 rr[g] = b->region_read_beg[g0 + g] - r0;
                 rh[g] = b->region_hap_beg[g0 + g] - h0;
+                rout[g] = acc;
+                if (g < n_regions)
+                    acc += (int64_t)(b->region_read_beg[g0 + g + 1] - b->region_read_beg[g0 + g]) *
+                           (b->region_hap_beg[g0 + g + 1] - b->region_hap_beg[g0 + g]);
             }
-            std::memcpy(hp + o_reg_out, out_beg.data(), sizeof(int64_t) * (p.n_regions + 1));
-            if (!long_pairs.empty()) std::memcpy(hp + o_long, long_pairs.data(), sizeof(LongPair) * long_pairs.size());
-            WarpJob* jd = (WarpJob*)(hp + o_jobs);
-            for (int k = 0; k < kSlots; k++)
-                if (!jobs_k[k].empty()) std::memcpy(jd + p.job_beg[k], jobs_k[k].data(), sizeof(WarpJob) * jobs_k[k].size());
         });
+    }
+    // the part as a batch of its own, over the packed copy: everything below reads this and not `b`
+    phmm_batch view{};
+    view.n_regions = n_regions; view.n_reads = n_reads; view.n_haps = n_haps;
+    view.region_read_beg = (const int32_t*)(hp + o_reg_read);
+    view.region_hap_beg = (const int32_t*)(hp + o_reg_hap);
+    view.read_off = (const int32_t*)(hp + o_read_off);
+    view.read_bases = hp + o_bases; view.read_q = hp + o_q;
+    view.read_i = general ? hp + o_gi : nullptr;
+    view.read_d = general ? hp + o_gd : nullptr;
+    view.read_c = general ? hp + o_gc : nullptr;
+    view.hap_off = (const int32_t*)(hp + o_hap_off);
+    view.hap_bases = hp + o_haps;
+    view.gap_open_i = gap[0]; view.gap_open_d = gap[1]; view.gap_cont_c = gap[2];
+    const auto t_packed = std::chrono::steady_clock::now();
+    CUDA_TRY(cudaMemcpyAsync(s.d_in.p, s.h_in.p, in_bytes, cudaMemcpyHostToDevice, s.stream));
+    if (copied) copied();                 // the submitter's arrays are no longer needed
+    b = nullptr;
+
+    // ---- phase B: plan on the packed copy, upload the jobs, launch ----
+    Plan plan;
+    {
+        int rcp = plan_part(&view, 0, n_regions, out0, dc.sm_count, dc.last_rescue_frac, pool, p, plan, err);
+        if (rcp) return rcp;
+        p.g0 = g0; p.g1 = g1; p.out0 = out0;
+    }
+    const std::vector<LongPair>& long_pairs = plan.long_pairs;
+    const std::vector<WarpJob>* jobs_k = plan.jobs_k;
+    const auto t_planned = std::chrono::steady_clock::now();
+    p.n_long = (int)long_pairs.size();
+    const size_t o_long = align_up(sizeof(WarpJob) * (size_t)p.n_jobs);
+    const size_t jobs_bytes = o_long + sizeof(LongPair) * long_pairs.size();
+    CUDA_TRY(s.h_jobs.reserve(jobs_bytes + 16));
+    CUDA_TRY(s.d_jobs.reserve(jobs_bytes + 16));
+    const size_t out_bytes = 16 + sizeof(float) * (size_t)p.n_pairs;
+    CUDA_TRY(s.h_out.reserve(out_bytes));
+    CUDA_TRY(s.d_out.reserve(out_bytes));
+    CUDA_TRY(s.d_rescue.reserve(sizeof(RescueOut) * (size_t)p.n_pairs));
+    CUDA_TRY(s.d_flags.reserve((size_t)p.n_jobs * p.hap_chunks + 16));
+    {
+        uint8_t* hj = (uint8_t*)s.h_jobs.p;
+        if (!long_pairs.empty()) std::memcpy(hj + o_long, long_pairs.data(), sizeof(LongPair) * long_pairs.size());
+        WarpJob* jd = (WarpJob*)hj;
+        for (int k = 0; k < kSlots; k++)
+            if (!jobs_k[k].empty()) std::memcpy(jd + p.job_beg[k], jobs_k[k].data(), sizeof(WarpJob) * jobs_k[k].size());
     }
 
     uint8_t* dp = (uint8_t*)s.d_in.p;
@@ -771,8 +820,8 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
     }
     a.hap_bases = dp + o_haps;
     a.ph2pr_f = dc.d_ph2pr_f; a.mm_f = dc.d_mm_f; a.ph2pr_d = dc.d_ph2pr_d; a.mm_d = dc.d_mm_d;
-    a.jobs = (const WarpJob*)(dp + o_jobs);
-    s.d_long = (const LongPair*)(dp + o_long);
+    a.jobs = (const WarpJob*)s.d_jobs.p;
+    s.d_long = (const LongPair*)((const uint8_t*)s.d_jobs.p + o_long);
     a.n_jobs = 0;
     a.haps_per_job = p.haps_per_job;
     a.stream_cap = (int32_t)((2 * (kSkew * 31 + 3) + (size_t)p.haps_per_job * (p.max_H + 1) + 127) / 128 * 128);
@@ -783,9 +832,8 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
     a.job_flags = (uint8_t*)s.d_flags.p;
     a.job_flag_base = 0;
 
-    const auto t_packed = std::chrono::steady_clock::now();
-    CUDA_TRY(cudaMemcpyAsync(s.d_in.p, s.h_in.p, in_bytes, cudaMemcpyHostToDevice, s.stream));
-    p.h2d_bytes = in_bytes;
+    if (jobs_bytes) CUDA_TRY(cudaMemcpyAsync(s.d_jobs.p, s.h_jobs.p, jobs_bytes, cudaMemcpyHostToDevice, s.stream));
+    p.h2d_bytes = in_bytes + jobs_bytes;
     if (!do_launch) return PHMM_OK;
 
     int rc = launch_kernels(s, exact, 1, 2, err);
@@ -796,8 +844,8 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
     if (trace) {
         const auto t_end = std::chrono::steady_clock::now();
         auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-        fprintf(stderr, "phmm trace: stage plan %.3f ms, pack %.3f ms, launch %.3f ms (%d jobs, %d launches, %lld pairs)\n",
-                ms(t_begin, t_planned), ms(t_planned, t_packed), ms(t_packed, t_end), p.n_jobs, p.launches, (long long)p.n_pairs);
+        fprintf(stderr, "phmm trace: stage pack %.3f ms | plan %.3f ms, launch %.3f ms (%d jobs, %d launches, %lld pairs)\n",
+                ms(t_begin, t_packed), ms(t_packed, t_planned), ms(t_planned, t_end), p.n_jobs, p.launches, (long long)p.n_pairs);
     }
     return PHMM_OK;
 }
@@ -807,6 +855,7 @@ int finalize_part(phmm_engine* e, DeviceCtx& dc, Slot& s, phmm_result* r, std::s
 {
     static const bool trace = getenv("PHMM_TRACE") != nullptr;
     Part& p = s.part;
+    if (s.async_rc) { err = s.async_err; return s.async_rc; }      // planning / launch failed after submit returned
     if (p.n_pairs == 0) return PHMM_OK;
     const auto t_begin = std::chrono::steady_clock::now();
     CUDA_TRY(cudaEventSynchronize(s.ev_done));
@@ -922,8 +971,8 @@ int init_device(DeviceCtx& dc, int depth, std::string& err)
 
 void free_slot(Slot& s)
 {
-    s.h_in.release(); s.h_out.release(); s.h_rescue.release();
-    s.d_in.release(); s.d_out.release(); s.d_rescue.release(); s.d_flags.release();
+    s.h_in.release(); s.h_jobs.release(); s.h_out.release(); s.h_rescue.release();
+    s.d_in.release(); s.d_jobs.release(); s.d_out.release(); s.d_rescue.release(); s.d_flags.release();
     for (int i = 0; i < kAuxStreams; i++) {
         if (s.ev_join[i]) cudaEventDestroy(s.ev_join[i]);
         if (s.aux[i]) cudaStreamDestroy(s.aux[i]);
@@ -1118,9 +1167,21 @@ int phmm_submit(phmm_engine* e, const phmm_batch* b, phmm_ticket* t)
         const int64_t out0 = batch_pairs(b, 0, cut[d]);
         const int g0 = cut[d], g1 = cut[d + 1];
         const bool exact = e->opt.exact_fp32 != 0;
-        dc.post([&, d, g0, g1, out0, exact] {
-            rcs[d] = stage_and_launch(*e->devs[d], e->devs[d]->slots[slot_of[d]], b, g0, g1, out0, exact, true, errs[d]);
-            latch.done();
+        s.async_rc = PHMM_OK; s.async_err.clear();
+        Slot* sp = &s;
+        DeviceCtx* dcp = &dc;
+        int* rc_out = &rcs[d];
+        std::string* err_out = &errs[d];
+        Latch* lp = &latch;
+        dc.post([=] {
+            // phase A of stage_and_launch ends with `copied`: from then on the submitter (and everything on
+            // its stack: rcs, errs, latch, the batch) is gone, and a failure is parked in the slot for phmm_wait
+            bool released = false;
+            std::string local_err;
+            const int rc = stage_and_launch(*dcp, *sp, b, g0, g1, out0, exact, true, local_err,
+                                            [&] { released = true; lp->done(); });
+            if (!released) { *rc_out = rc; *err_out = local_err; lp->done(); }
+            else if (rc) { sp->async_rc = rc; sp->async_err = local_err; }
         });
         rec.parts.emplace_back(d, slot_of[d]);
     }
