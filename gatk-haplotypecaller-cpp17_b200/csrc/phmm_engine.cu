@@ -477,6 +477,8 @@ int plan_part(const phmm_batch* b, int g0, int g1, int64_t out0, int sm_count, f
               HostPool& pool, Part& p, Plan& plan, std::string& err)
 {
     (void)err;
+    static const bool trace_plan = getenv("PHMM_TRACE_PLAN") != nullptr;
+    const auto tp0 = std::chrono::steady_clock::now();
     p = Part();
     p.g0 = g0; p.g1 = g1; p.out0 = out0;
     p.n_regions = g1 - g0;
@@ -536,9 +538,11 @@ int plan_part(const phmm_batch* b, int g0, int g1, int64_t out0, int sm_count, f
         for (int R = 1; R <= kMaxReadLenCompiled; R++)
             packed_on[R] = n_of_len[R] >= 256 && n_of_len[R] * 10 >= p.n_reads && packed_shape(R, nullptr) >= 0;
     }
+    const auto tp1 = std::chrono::steady_clock::now();
     pool.parallel_for(n_pieces, [&](int t) {
         PlanPiece& pc = pieces[t];
-        std::vector<std::pair<int, int>> by_len;         // (read length, read index within the part)
+        std::vector<std::pair<int, int>> by_len, sorted;  // (read length, read index within the part)
+        pc.planned.reserve((size_t)(b->region_read_beg[piece_cut[t + 1]] - b->region_read_beg[piece_cut[t]]) / 3 + 16);
         for (int g = piece_cut[t]; g < piece_cut[t + 1]; g++) {
             const int nh = b->region_hap_beg[g + 1] - b->region_hap_beg[g];
             pc.max_nh = std::max(pc.max_nh, nh);
@@ -578,9 +582,15 @@ int plan_part(const phmm_batch* b, int g0, int g1, int64_t out0, int sm_count, f
                 pc.n_jobs_sh[sh]++; pc.n_aligned_sh[sh]++;
                 pc.planned.push_back(pj);
             }
-            std::sort(by_len.begin(), by_len.end(), [](const std::pair<int, int>& x, const std::pair<int, int>& y) {
-                return x.first != y.first ? x.first > y.first : x.second < y.second;
-            });
+            {   // longest first, ties in read order: a stable counting sort over the 255 possible lengths
+                int first_of_len[kMaxReadLenCompiled + 2] = {0};
+                for (const auto& x : by_len) first_of_len[x.first]++;
+                int acc = 0;
+                for (int R = kMaxReadLenCompiled; R >= 1; R--) { const int c = first_of_len[R]; first_of_len[R] = acc; acc += c; }
+                sorted.resize(by_len.size());
+                for (const auto& x : by_len) sorted[first_of_len[x.first]++] = x;
+                by_len.swap(sorted);
+            }
             for (size_t i = 0; i < by_len.size();) {
                 const int sh = pick_shape(by_len[i].first, h_avg);
                 const int cap = 2 * (32 / kShapes[sh].G);
@@ -598,6 +608,7 @@ int plan_part(const phmm_batch* b, int g0, int g1, int64_t out0, int sm_count, f
             }
         }
     });
+    const auto tp2 = std::chrono::steady_clock::now();
     std::vector<LongPair>& long_pairs = plan.long_pairs;
     long_pairs.clear();
     int64_t n_jobs_sh[kNumShapes] = {0}, n_aligned_sh[kNumShapes] = {0};
@@ -661,6 +672,12 @@ int plan_part(const phmm_batch* b, int g0, int g1, int64_t out0, int sm_count, f
         const bool dense = last_rescue_frac > 0.05f;
         p.haps_per_job64 = dense ? hpj : 1;
         p.hap_chunks64 = (nhm + p.haps_per_job64 - 1) / p.haps_per_job64;
+    }
+    if (trace_plan) {
+        const auto tp3 = std::chrono::steady_clock::now();
+        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "phmm plan trace: setup %.3f ms, pieces %.3f ms (%d), merge + chunk model %.3f ms\n",
+                ms(tp0, tp1), ms(tp1, tp2), n_pieces, ms(tp2, tp3));
     }
 
     return PHMM_OK;
