@@ -232,8 +232,20 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # stdout carries the one JSON line only: NCCL's banner (printed by the C library on communicator
+        # creation when NCCL_DEBUG is set) goes to stderr -- file descriptor 1 points at stderr while the
+        # communicator is created (eagerly, device_id given, and again under the first collective)
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     from __graft_entry__ import load_package
     pkg = load_package()
