@@ -11,10 +11,10 @@
 //     column per lane) is K cell updates against 3 shuffled values (the bottom row handed to lane
 //     l+1), instead of 3 lane shifts per cell;
 //   * the FP32 kernel packs TWO reads (same haplotype) into the two halves of f32x2 registers
-//     (FFMA2/FMUL2/FADD2 on sm_100): 8 packed FP32-pipe instructions update two cells, which frees
-//     issue slots for the 2 LOP3 + 2 FSEL per cell pair that pick the match/mismatch prior
-//     (measured on B200: FFMA and FFMA2 both saturate at ~125 lane-FMAs/clk/SM, integer/select ops
-//     at 64/clk/SM -- profiles/r01_microbench_pipes.txt);
+//     (FFMA2/FMUL2/FADD2 on sm_100): 7-8 packed FP32-pipe instructions update two cells, half the
+//     instruction stream of the scalar form for the same FP32 throughput (measured on B200: FFMA and
+//     FFMA2 both saturate at ~125 lane-FMAs/clk/SM -- profiles/r01_microbench_pipes.txt), so shuffles,
+//     loads and loop overhead are amortised over twice the work;
 //   * the match/mismatch prior (avx-pairhmm-template.h:3-35,70-75,152-158) is NOT selected with
 //     integer/select instructions: ncu showed every LOP3/FSEL paying 1-2 extra dispatch-stall cycles
 //     behind the FFMA2s (register-file read ports), ~30% of the kernel.  Instead each read pair gets
@@ -35,7 +35,12 @@
 //     reproduce row 0 of the reference (M = X = 0, Y = INITIAL_CONSTANT/haplen,
 //     avx-pairhmm-template.h:86-92,161-175) exactly (priors 0, Y self-transition 1), so the last
 //     read row is always the last row of the last lane and the final sum (:328-343) is a running
-//     sum in that lane, in the reference's column order.
+//     sum in that lane, in the reference's column order.  Two faster layouts exist for reads that are a
+//     whole number of lanes (ALIGNED: dummy rows fill whole lanes; PACKED: lane groups of any width,
+//     no dummy rows at all) -- see the kernel's comment;
+//   * three precision tiers: FP32 (ftz), FP64 redo of FP32 underflows, flush-exact FP64 redo of the
+//     pairs that end near the double denormal range (kFlushDanger).  Reads beyond 255 bases take
+//     phmm_long.cu.
 //
 // Arithmetic: default is FMA-contracted (8 FP32-pipe instructions per cell: the roofline unit of
 // SURVEY.md section 8d); EXACT=true uses unfused mul/add in the reference's operation order and
