@@ -20,6 +20,7 @@ LIB_PATH = os.environ.get("PHMM_LIB", os.path.join(_HERE, "libphmm_b200.so"))   
 CSRC = os.path.join(_HERE, "csrc")
 
 PHMM_OK = 0
+PHMM_ERR_UNSUPPORTED = 5
 ERR_NAMES = {1: "INVALID_ARG", 2: "NO_DEVICE", 3: "CUDA", 4: "OOM", 5: "UNSUPPORTED", 6: "BAD_TICKET"}
 
 
@@ -72,7 +73,7 @@ class _Result(C.Structure):
 EXPORTS = ["phmm_create", "phmm_destroy", "phmm_compute", "phmm_submit", "phmm_wait", "phmm_strerror",
            "phmm_last_error", "phmm_abi_version", "phmm_normalize_filter", "phmm_tables",
            "phmm_stage", "phmm_run_staged", "phmm_run_staged_ex", "phmm_run_staged_pipelined",
-           "phmm_fetch_staged", "phmm_free_staged", "phmm_plan"]
+           "phmm_fetch_staged", "phmm_free_staged", "phmm_plan", "phmm_sw_align"]
 
 class _PlanInfo(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("mode", C.c_int32), ("n_jobs", C.c_int32), ("n_long_pairs", C.c_int32),
@@ -80,6 +81,49 @@ class _PlanInfo(C.Structure):
                 ("hap_chunks64", C.c_int32), ("n_pairs", C.c_int64), ("n_cells", C.c_int64), ("n_shapes", C.c_int32),
                 ("shape_g", C.c_int32 * 32), ("shape_k", C.c_int32 * 32),
                 ("jobs_ragged", C.c_int32 * 32), ("jobs_aligned", C.c_int32 * 32)]
+
+
+class _SwBatch(C.Structure):
+    _fields_ = [("n", C.c_int32), ("ref_off", C.c_void_p), ("ref_bases", C.c_void_p), ("alt_off", C.c_void_p),
+                ("alt_bases", C.c_void_p), ("w_match", C.c_int32), ("w_mismatch", C.c_int32), ("w_open", C.c_int32),
+                ("w_extend", C.c_int32)]
+
+
+class _SwResult(C.Structure):
+    _fields_ = [("offset", C.c_void_p), ("elem_beg", C.c_void_p), ("cap_elems", C.c_int64), ("ops", C.c_void_p),
+                ("lens", C.c_void_p), ("kernel_ms", C.c_float)]
+
+
+SW_NEW_PARAMETERS = (200, -150, -260, -11)     # IntelSWAligner::NEW_SW_PARAMETERS, the default of align()
+
+
+def sw_align(pairs, params=SW_NEW_PARAMETERS, device=0, cap_elems=None):
+    """phmm_sw_align: Smith-Waterman haplotype -> reference alignment of a batch of (ref, alt) byte strings,
+    as hc::IntelSWAligner::align does one at a time.  Returns ([(offset, cigar string)], kernel_ms)."""
+    n = len(pairs)
+    refs = [np.frombuffer(bytes(r), np.uint8) for r, _ in pairs]
+    alts = [np.frombuffer(bytes(a), np.uint8) for _, a in pairs]
+    cat = lambda xs: np.ascontiguousarray(np.concatenate(xs)) if xs else np.zeros(0, np.uint8)
+    off = lambda xs: np.concatenate([[0], np.cumsum([len(x) for x in xs])]).astype(np.int32)
+    ref_off, alt_off, ref_b, alt_b = off(refs), off(alts), cat(refs), cat(alts)
+    worst = int(ref_off[-1]) + int(alt_off[-1]) + 2 * n
+    cap = min(worst, 32 * n + 4096) if cap_elems is None else cap_elems
+    while True:
+        offset = np.zeros(n, np.int32); elem_beg = np.zeros(n + 1, np.int64)
+        ops = np.zeros(max(cap, 1), np.uint8); lens = np.zeros(max(cap, 1), np.int32)
+        b = _SwBatch(n, ref_off.ctypes.data, ref_b.ctypes.data, alt_off.ctypes.data, alt_b.ctypes.data, *params)
+        r = _SwResult(offset.ctypes.data, elem_beg.ctypes.data, cap, ops.ctypes.data, lens.ctypes.data, 0.0)
+        rc = lib().phmm_sw_align(device, C.byref(b), C.byref(r))
+        if rc == PHMM_ERR_UNSUPPORTED and cap_elems is None and cap < worst and \
+                max(len(x) for x in refs + alts) <= 1023:
+            cap = worst                                   # unusually fragmented CIGARs: retry with the worst case
+            continue
+        if rc != PHMM_OK:
+            raise PhmmError(rc, lib().phmm_strerror(rc).decode())
+        break
+    ch = ops.tobytes().decode("latin1")
+    out = [(int(offset[k]), "".join(f"{lens[e]}{ch[e]}" for e in range(int(elem_beg[k]), int(elem_beg[k + 1])))) for k in range(n)]
+    return out, float(r.kernel_ms)
 
 
 _lib = None
@@ -110,6 +154,7 @@ def lib():
         L.phmm_run_staged_pipelined.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int32,
                                                 C.POINTER(C.c_float), C.POINTER(C.c_int32)]
         L.phmm_plan.argtypes = [C.POINTER(_Batch), C.c_int32, C.c_int32, C.POINTER(_PlanInfo), C.c_void_p, C.c_int64]
+        L.phmm_sw_align.argtypes = [C.c_int32, C.POINTER(_SwBatch), C.POINTER(_SwResult)]
         L.phmm_fetch_staged.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_Result)]
         L.phmm_free_staged.argtypes = [C.c_void_p, C.c_void_p]; L.phmm_free_staged.restype = None
         _lib = L

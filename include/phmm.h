@@ -184,6 +184,40 @@ int  phmm_run_staged_pipelined(phmm_engine* e, phmm_staged* const* staged, int32
 int  phmm_fetch_staged(phmm_engine* e, phmm_staged* s, phmm_result* r);
 void phmm_free_staged(phmm_engine* e, phmm_staged* s);
 
+/*
+ * Smith-Waterman haplotype -> reference alignment with back-track: a batch of
+ * (reference window, haplotype) pairs, each scored exactly like hc::IntelSWAligner::align
+ * (smithwaterman/intel_smithwaterman.hpp:29-44): all-match shortcut (equal length, <= 2 mismatches ->
+ * offset 0, "<len>M"), otherwise runSWOnePairBT_avx2 (native/PairWiseSW.h:41-447) with the SOFTCLIP
+ * overhang strategy.  Integer arithmetic, bit-exact: same CIGAR, same offset.  Independent of phmm_engine
+ * (takes a CUDA device ordinal); synchronous.  Sequences longer than PHMM_SW_MAX_LEN (the reference's
+ * MAX_SEQ_LEN, where its own arrays end) -> PHMM_ERR_UNSUPPORTED; empty ones -> PHMM_ERR_INVALID_ARG (the
+ * reference throws); no device -> PHMM_ERR_NO_DEVICE (there is no CPU fallback).
+ *   alignment k: reference bytes [ref_off[k], ref_off[k+1]) of ref_bases, haplotype bytes
+ *   [alt_off[k], alt_off[k+1]) of alt_bases.  Output: offset[k] (alignment begin in the reference) and the
+ *   CIGAR elements [elem_beg[k], elem_beg[k+1]) of the compact arrays ops / lens, ops in {'M','I','D','S'},
+ *   in CIGAR order.  More than cap_elems elements in total -> PHMM_ERR_UNSUPPORTED (retry with more room;
+ *   sum(nref + nalt) always suffices).
+ */
+#define PHMM_SW_MAX_LEN 1023     /* the reference indexes E[MAX_SEQ_LEN - nrow - 1] and 2*MAX_SEQ_LEN^2 back-track words */
+typedef struct phmm_sw_batch {
+    int32_t n;
+    const int32_t* ref_off;           /* [n+1] */
+    const uint8_t* ref_bases;
+    const int32_t* alt_off;           /* [n+1] */
+    const uint8_t* alt_bases;
+    int32_t w_match, w_mismatch, w_open, w_extend;   /* IntelSWAligner::SWParameters; NEW_SW_PARAMETERS = 200,-150,-260,-11 */
+} phmm_sw_batch;
+typedef struct phmm_sw_result {
+    int32_t* offset;                  /* [n]                                                   */
+    int64_t* elem_beg;                /* [n+1] out                                             */
+    int64_t  cap_elems;               /* capacity of ops / lens, >= n                          */
+    uint8_t* ops;                     /* [cap_elems]                                           */
+    int32_t* lens;                    /* [cap_elems]                                           */
+    float    kernel_ms;               /* out: device time of the alignment kernels (CUDA events) */
+} phmm_sw_result;
+int  phmm_sw_align(int32_t device, const phmm_sw_batch* b, phmm_sw_result* r);
+
 #ifdef __cplusplus
 }
 #endif

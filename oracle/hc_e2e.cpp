@@ -42,6 +42,11 @@
 #ifdef HC_USE_B200
 #define IntelPairHMM B200PairHMM
 #endif
+#ifdef HC_USE_B200_SW       // hc_e2e_b200_sw: the haplotype -> reference aligner swapped too, same trick:
+#include "smithwaterman/intel_smithwaterman.hpp"      // the reference's header first (#pragma once), then the
+#include "b200_smithwaterman.hpp"                     // token IntelSWAligner names hc::B200SWAligner inside
+#define IntelSWAligner B200SWAligner                  // assembler/graph_wrapper.hpp:232-239
+#endif
 #ifdef HC_BATCHED
 #define private public      // the batched driver below calls the reference's own private helpers
 #endif                      // (load_all_reads, select_one_read, filter_reads, hard_clip_reads)
@@ -164,7 +169,9 @@ int main(int argc, char** argv)
 #endif
         const auto t2 = std::chrono::steady_clock::now();
         std::fprintf(stderr, "hc_e2e: engine=%s init_s=%.3f do_work_s=%.3f\n",
-#if defined(HC_BATCHED)
+#if defined(HC_USE_B200_SW)
+                     "b200+sw",
+#elif defined(HC_BATCHED)
                      "b200-batched",
 #elif defined(HC_USE_B200)
                      "b200",

@@ -27,6 +27,7 @@
 #include <cstring>
 
 #include "pairhmm/intel_pairhmm.hpp"   // pulls native/avx-pairhmm.h, sam.hpp, haplotype.hpp
+#include "smithwaterman/intel_smithwaterman.hpp"   // the reference's SW aligner
 
 namespace {
 Context<float>*  g_f = nullptr;
@@ -159,6 +160,19 @@ int ref_compute_likelihoods(int n_reads, const int32_t* read_off, const uint8_t*
         for (int h = 0; h < n_haps; h++) lik_out[k * n_haps + h] = lik[k][h];
     }
     return (int)reads.size();
+}
+
+// hc::IntelSWAligner::align (smithwaterman/intel_smithwaterman.hpp:29-44) with explicit weights; returns
+// the alignment offset and writes the CIGAR string.
+int ref_sw_align(const uint8_t* ref, int nref, const uint8_t* alt, int nalt,
+                 int w_match, int w_mismatch, int w_open, int w_extend, char* cigar, int cap)
+{
+    hc::IntelSWAligner aligner;
+    hc::IntelSWAligner::SWParameters prm{w_match, w_mismatch, w_open, w_extend};
+    auto [off, cg] = aligner.align(std::string_view((const char*)ref, (size_t)nref),
+                                   std::string_view((const char*)alt, (size_t)nalt), prm);
+    std::snprintf(cigar, (size_t)cap, "%s", cg.to_string().c_str());
+    return (int)off;
 }
 
 } // extern "C"
