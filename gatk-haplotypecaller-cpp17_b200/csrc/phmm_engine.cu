@@ -642,7 +642,7 @@ int plan_part(const phmm_batch* b, int g0, int g1, int64_t out0, int sm_count, f
         // ragged window stream: single-shape kernels took one such job's duration).  Makespan model over the
         // candidates: all steps / resident warps + the longest unit; overhead per chunk ~128 steps.
         const int nhm = std::max(1, p.max_nh);
-        const int by_smem = std::max(1, (kSmemBytesPerWarpBudget - 2 * (kSkew * 31 + 3) - 16) / (p.max_H + 1 + kPerHapTableBytes));
+        const int by_smem = std::max(1, (kSmemBytesPerWarpBudget - 2 * (kSkew * 31 + 3) - 16) / (p.max_H + 2 + kPerHapTableBytes));   // + NEXT (+ NEXT2)
         std::vector<int64_t> jobs_with_nh(nhm + 1, 0);
         for (const PlanPiece& pc : pieces)
             for (const PlannedJob& pj : pc.planned) {
@@ -841,7 +841,7 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
     s.d_long = (const LongPair*)((const uint8_t*)s.d_jobs.p + o_long);
     a.n_jobs = 0;
     a.haps_per_job = p.haps_per_job;
-    a.stream_cap = (int32_t)((2 * (kSkew * 31 + 3) + (size_t)p.haps_per_job * (p.max_H + 1) + 127) / 128 * 128);
+    a.stream_cap = (int32_t)((2 * (kSkew * 31 + 3) + (size_t)p.haps_per_job * (p.max_H + 2) + 127) / 128 * 128);
     a.smem_bytes_per_warp = 0;    // set per shape at launch (the prior tables depend on K and G)
     a.rescue_count = (unsigned*)s.d_out.p;
     a.raw32 = (float*)((uint8_t*)s.d_out.p + 16);

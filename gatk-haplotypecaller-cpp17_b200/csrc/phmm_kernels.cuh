@@ -242,7 +242,7 @@ __device__ __forceinline__ int base_code(uint8_t b) {
 __host__ __device__ constexpr int lane_units(int K) { return (((K + 1) / 2) % 2) ? (K + 1) / 2 : (K + 1) / 2 + 1; }
 __host__ __device__ constexpr int subtable_bytes(int K, int G) { return (G * lane_units(K) * 16 + 127) / 128 * 128; }
 __host__ __device__ constexpr int tables_bytes(int K, int G) { return (32 / G) * 5 * subtable_bytes(K, G); }
-constexpr int kStreamNext = 0x80, kStreamIdle = 0x81;   // stream bytes >= 0x80 are not columns
+constexpr int kStreamNext = 0x80, kStreamIdle = 0x81, kStreamNext2 = 0x82;   // stream bytes >= 0x80 are not columns
 
 // ---- the forward kernel ----------------------------------------------------------------------
 //
@@ -275,6 +275,14 @@ forward_kernel(const KernelArgs args)
 {
     static_assert(!ALIGNED || MODE != kModeGeneral, "ALIGNED needs batch-constant gap penalties");
     static_assert(!PACKED || (ALIGNED && G == 32), "PACKED is a variant of ALIGNED on the whole warp");
+    // ZRESET (the lane-aligned layouts): a lane does not RESET its registers between two haplotypes, it runs
+    // two ordinary cell steps with its transition factors zeroed (stream bytes NEXT, NEXT2).  The recurrence
+    // is linear in the state: with pMM = pGAPM = 0 the first step gives M = Pm = 0 (and X = 0, because the
+    // lane above sent zeros one step earlier) and leaves Y = old Pm, the second, with pYY = 0 too, clears Y.
+    // The straddling steps between haplotypes then cost one cell step each instead of a divergent ~150-
+    // instruction reset block per lane (ncu: those 3% of the steps were 7% of the launch); idle bytes are
+    // zero steps as well, so the straddling loop has no branch but the last lane's hand-over of its sums.
+    constexpr bool ZRESET = ALIGNED;
     using S = typename P::S;
     using V = typename P::V;
     constexpr int NH = P::NH;
@@ -456,10 +464,11 @@ forward_kernel(const KernelArgs args)
                 sb[pos + j] = (uint8_t)(base_code(args.hap_bases[ho + j]) * (SUBT / 128));
             if (lane == 0) {
                 sb[pos + H] = (uint8_t)kStreamNext;
+                if (ZRESET) sb[pos + H + 1] = (uint8_t)kStreamNext2;
                 s_inity[n] = P::sdiv(P::init_const(), (S)H);   // avx-pairhmm-template.h:86
                 s_hidx[n] = h; s_apos[n] = pos; s_alen[n] = H;
             }
-            pos += H + 1; ++n;
+            pos += H + 1 + (ZRESET ? 1 : 0); ++n;
         }
         if (n == 0) continue;
         for (int j = lane; j < LEAD; j += 32) sb[j] = (uint8_t)kStreamIdle;
@@ -498,7 +507,7 @@ forward_kernel(const KernelArgs args)
         // products: EXACT ones honour the reference's flush-to-zero in both precisions (P::mulx)
         auto MUL = [](const V a, const V b) { return EXACT ? P::mulx(a, b) : P::mul(a, b); };
         // K cell updates of this lane's current column; `cb` is the column's stream byte
-        auto cells = [&](const uint32_t cb) {
+        auto cells = [&](const uint32_t cb, const V fMM, const V fG, const V fYY, const V fMM0, const V fGX0) {
             // priors of this column: K entries of the sub-table the haplotype base names.  Issued
             // first; phase A below (4K FP32-pipe instructions) covers the LDS latency.
             V prior[K + 1];
@@ -514,13 +523,16 @@ forward_kernel(const KernelArgs args)
                 const V dM = k ? M[k - 1] : dgM;            // (row-1, c-1)
                 const V dX = k ? X[k - 1] : dgX;
                 const V dY = k ? Y[k - 1] : dgY;
-                const V cMM = (PACKED && k == 0) ? pMM0 : pMM[kk];
-                const V cGX = (PACKED && k == 0) ? pGAPX0 : pGAPM[kk];
+                // ZRESET: the factors come as arguments (uniform in the steady loop, zeroed per lane at the
+                // NEXT / NEXT2 / idle bytes of the straddling loop)
+                const V cMM = (PACKED && k == 0) ? fMM0 : (ZRESET ? fMM : pMM[kk]);
+                const V cGX = (PACKED && k == 0) ? fGX0 : (ZRESET ? fG : pGAPM[kk]);
+                const V cGY = ZRESET ? fG : pGAPM[kk];
                 if (EXACT) {
                     // reference operation order, unfused (avx-pairhmm-template.h:188)
-                    t0[k] = P::addx(P::addx(MUL(dM, cMM), MUL(dX, cGX)), MUL(dY, pGAPM[kk]));
+                    t0[k] = P::addx(P::addx(MUL(dM, cMM), MUL(dX, cGX)), MUL(dY, cGY));
                 } else {
-                    t0[k] = P::fma(dY, pGAPM[kk], P::fma(dX, cGX, MUL(dM, cMM)));
+                    t0[k] = P::fma(dY, cGY, P::fma(dX, cGX, MUL(dM, cMM)));
                 }
             }
             // Y from the left neighbour (:197); needs M of the previous column
@@ -528,7 +540,7 @@ forward_kernel(const KernelArgs args)
             for (int k = 0; k < K; ++k) {
                 const int kk = CONSTG ? 0 : k;
                 const V yv = SHARED ? Pm[k] : MUL(M[k], pMY[kk]);
-                const V cYY = ALIGNED ? pXXc : pYY[ALIGNED ? 0 : k];
+                const V cYY = ALIGNED ? fYY : pYY[ALIGNED ? 0 : k];
                 Y[k] = EXACT ? P::addx(yv, MUL(Y[k], cYY)) : P::fma(Y[k], cYY, yv);
             }
             // Phase B: M = t0 * prior (:152-158, :188)
@@ -569,8 +581,8 @@ forward_kernel(const KernelArgs args)
             }
         };
         // a haplotype ends for this lane
-        auto boundary = [&]() {
-            if (l == nl - 1) {
+        auto emit = [&]() {
+            {
                 const int h = s_hidx[jcur];
 #pragma unroll
                 for (int hf = 0; hf < NH; ++hf) {
@@ -593,6 +605,9 @@ forward_kernel(const KernelArgs args)
                     }
                 }
             }
+        };
+        auto boundary = [&]() {
+            if (l == nl - 1) emit();
             ++jcur;
             inity_cur = s_inity[min(jcur, n - 1)];
             reset_state(inity_cur);
@@ -602,8 +617,8 @@ forward_kernel(const KernelArgs args)
 
         // shared address of this lane's byte at step t is bp + t
         const uint32_t bp = (uint32_t)__cvta_generic_to_shared(sb) + (uint32_t)(kSkew * (nl - 1 - l));
-        int t = 0;
-        uint32_t b_next = lds_u8(bp);
+        int t = PACKED ? LEAD - 1 - kSkew * (nl - 1) : 0;   // PACKED: skip the steps in which no lane has work yet
+        uint32_t b_next = lds_u8(bp + (uint32_t)t);
 #pragma unroll 1
         for (int j = 0; j <= n; ++j) {
             // [t_a, t_s): every lane of the group is inside haplotype j -> no tests at all
@@ -614,15 +629,29 @@ forward_kernel(const KernelArgs args)
             for (; t < t_a; ++t) {
                 const uint32_t bcur = b_next;
                 b_next = lds_u8(bp + (uint32_t)(t + 1));
-                if (bcur < 0x80u) cells(bcur);
-                else if (bcur == (uint32_t)kStreamNext) boundary();
+                if (ZRESET) {
+                    const bool zs = bcur >= 0x80u;                  // NEXT, NEXT2 or idle: a zero step
+                    if (bcur == (uint32_t)kStreamNext) {            // this lane has seen the last column of its haplotype
+                        if (l == nl - 1) emit();
+                        ++jcur;
+                        inity_cur = s_inity[min(jcur, n - 1)];
+                        sumM = P::splat(0); sumX = P::splat(0);
+                        if (PACKED && top) { inY = P::splat(inity_cur); if (kSkew == 2) qY = inY; }
+                    }
+                    const V z = P::splat(0);
+                    // a zero step reads the lane's own 'A' sub-table: any FINITE priors do (0 * prior must be 0)
+                    cells(zs ? 0u : bcur, zs ? z : pMM[0], zs ? z : pGAPM[0], zs ? z : pXXc, zs ? z : pMM0, zs ? z : pGAPX0);
+                } else {
+                    if (bcur < 0x80u) cells(bcur, pMM[0], pGAPM[0], pXXc, pMM0, pGAPX0);
+                    else if (bcur == (uint32_t)kStreamNext) boundary();
+                }
                 rotate();
             }
 #pragma unroll 4
             for (; t < t_s; ++t) {
                 const uint32_t bcur = b_next;
                 b_next = lds_u8(bp + (uint32_t)(t + 1));
-                cells(bcur);
+                cells(bcur, pMM[0], pGAPM[0], pXXc, pMM0, pGAPX0);
                 rotate();
             }
         }
