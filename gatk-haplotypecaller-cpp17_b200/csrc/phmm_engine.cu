@@ -235,6 +235,15 @@ struct Slot {
     DeviceBuf d_in, d_jobs, d_out, d_rescue, d_flags;
     int async_rc = PHMM_OK;                  // failure after the submitter was released: reported by phmm_wait
     std::string async_err;
+    struct StageCtx {                        // what the pack phase hands to the plan + launch phase
+        size_t o_read_off = 0, o_hap_off = 0, o_reg_read = 0, o_reg_hap = 0, o_reg_out = 0, o_bases = 0, o_q = 0,
+               o_gi = 0, o_gd = 0, o_gc = 0, o_haps = 0, in_bytes = 0;
+        phmm_batch view{};                   // the part as a batch of its own, over the packed copy
+        bool general = false, empty = true;
+        int g0 = 0, g1 = 0;
+        int64_t out0 = 0;
+        std::chrono::steady_clock::time_point t_begin, t_packed;
+    } stage;
     bool busy = false;
     Part part;
     KernelArgs args{};
@@ -252,31 +261,42 @@ struct DeviceCtx {
     int next_slot = 0;
     float* d_ph2pr_f = nullptr; float* d_mm_f = nullptr;
     double* d_ph2pr_d = nullptr; double* d_mm_d = nullptr;
-    // worker
-    std::thread worker;
-    std::mutex mu;
-    std::condition_variable cv;
-    std::deque<std::function<void()>> queue;
-    bool stop = false;
-
-    void run() {
-        cudaSetDevice(ordinal);
-        for (;;) {
-            std::function<void()> fn;
-            {
-                std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&] { return stop || !queue.empty(); });
-                if (queue.empty()) return;
-                fn = std::move(queue.front());
-                queue.pop_front();
+    // Two threads per device.  The WORKER plans, launches and finalizes (and serves the staged form); the
+    // PACKER only copies a submitter's arrays into pinned staging and starts their upload, so that a
+    // submitter is never held up behind the planning or the log10 pass of an earlier batch.
+    struct WorkQueue {
+        std::thread th;
+        std::mutex mu;
+        std::condition_variable cv;
+        std::deque<std::function<void()>> queue;
+        bool stop = false;
+        void run(int ordinal) {
+            cudaSetDevice(ordinal);
+            for (;;) {
+                std::function<void()> fn;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return stop || !queue.empty(); });
+                    if (queue.empty()) return;
+                    fn = std::move(queue.front());
+                    queue.pop_front();
+                }
+                fn();
             }
-            fn();
         }
-    }
-    void post(std::function<void()> fn) {
-        { std::lock_guard<std::mutex> lk(mu); queue.push_back(std::move(fn)); }
-        cv.notify_one();
-    }
+        void post(std::function<void()> fn) {
+            { std::lock_guard<std::mutex> lk(mu); queue.push_back(std::move(fn)); }
+            cv.notify_one();
+        }
+        void start(int ordinal) { th = std::thread([this, ordinal] { run(ordinal); }); }
+        void finish() {
+            { std::lock_guard<std::mutex> lk(mu); stop = true; }
+            cv.notify_all();
+            if (th.joinable()) th.join();
+        }
+    };
+    WorkQueue worker, packer;
+    void post(std::function<void()> fn) { worker.post(std::move(fn)); }
 };
 
 struct Latch {
@@ -689,11 +709,20 @@ int plan_part(const phmm_batch* b, int g0, int g1, int64_t out0, int sm_count, f
 //   B (reads only the packed copy): plan (plan_part on a view of the pinned block), upload the job list,
 //     launch, start the download.  Runs while the submitter validates and packs its next batch and while the
 //     data upload is in flight; a failure here is kept in the slot and reported by phmm_wait.
-int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1, int64_t out0,
-                     bool exact, bool do_launch, std::string& err, const std::function<void()>& copied = {})
+// Regions [g0,g1) of the batch on one device, in two phases.
+//   stage_pack   (reads the caller's arrays; the device's PACKER thread): pack them into the slot's pinned
+//                block -- offsets rebased to the part -- and start its upload.  After it the submitter is
+//                released and may free or reuse its arrays.
+//   stage_launch (reads only the packed copy; the device's WORKER thread): plan (plan_part on a view of the
+//                pinned block), upload the job list, launch, start the download.  Runs while the submitter
+//                validates and packs its next batch and while the data upload is in flight; a failure here
+//                is kept in the slot and reported by phmm_wait.
+int stage_pack(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1, int64_t out0, std::string& err)
 {
-    static const bool trace = getenv("PHMM_TRACE") != nullptr;      // development aid: host time per phase
-    const auto t_begin = std::chrono::steady_clock::now();
+    Slot::StageCtx& c = s.stage;
+    c = Slot::StageCtx();
+    c.t_begin = std::chrono::steady_clock::now();
+    c.g0 = g0; c.g1 = g1; c.out0 = out0;
     Part& p = s.part;
     p = Part();
     p.g0 = g0; p.g1 = g1; p.out0 = out0;
@@ -704,12 +733,14 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
     const int n_reads = r1 - r0, n_haps = h1 - h0, n_regions = g1 - g0;
     p.n_reads = n_reads; p.n_haps = n_haps;
     p.n_pairs = batch_pairs(b, g0, g1);
-    if (p.n_pairs == 0) { if (copied) copied(); return PHMM_OK; }
+    if (p.n_pairs == 0) return PHMM_OK;
+    c.empty = false;
     const int rb0 = b->read_off[r0], rb1 = b->read_off[r1];
     const int hb0 = b->hap_off[h0], hb1 = b->hap_off[h1];
     const size_t read_bytes = (size_t)(rb1 - rb0), hap_bytes = (size_t)(hb1 - hb0);
     uint8_t gap[3];
     const bool general = detect_gap_mode(b, rb0, rb1, gap) == kModeGeneral;
+    c.general = general;
 
     // ---- phase A: layout of the data block, pack, upload ----
     size_t off = 0;
@@ -766,8 +797,12 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
             }
         });
     }
+    c.o_read_off = o_read_off; c.o_hap_off = o_hap_off; c.o_reg_read = o_reg_read; c.o_reg_hap = o_reg_hap;
+    c.o_reg_out = o_reg_out; c.o_bases = o_bases; c.o_q = o_q; c.o_gi = o_gi; c.o_gd = o_gd; c.o_gc = o_gc;
+    c.o_haps = o_haps; c.in_bytes = in_bytes;
     // the part as a batch of its own, over the packed copy: everything below reads this and not `b`
-    phmm_batch view{};
+    phmm_batch& view = c.view;
+    view = phmm_batch{};
     view.n_regions = n_regions; view.n_reads = n_reads; view.n_haps = n_haps;
     view.region_read_beg = (const int32_t*)(hp + o_reg_read);
     view.region_hap_beg = (const int32_t*)(hp + o_reg_hap);
@@ -779,11 +814,26 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
     view.hap_off = (const int32_t*)(hp + o_hap_off);
     view.hap_bases = hp + o_haps;
     view.gap_open_i = gap[0]; view.gap_open_d = gap[1]; view.gap_cont_c = gap[2];
-    const auto t_packed = std::chrono::steady_clock::now();
+    c.t_packed = std::chrono::steady_clock::now();
     CUDA_TRY(cudaMemcpyAsync(s.d_in.p, s.h_in.p, in_bytes, cudaMemcpyHostToDevice, s.stream));
-    if (copied) copied();                 // the submitter's arrays are no longer needed
-    b = nullptr;
+    return PHMM_OK;                       // the submitter's arrays are no longer needed
+}
 
+int stage_launch(DeviceCtx& dc, Slot& s, bool exact, bool do_launch, std::string& err)
+{
+    static const bool trace = getenv("PHMM_TRACE") != nullptr;      // development aid: host time per phase
+    Slot::StageCtx& c = s.stage;
+    if (c.empty) return PHMM_OK;
+    Part& p = s.part;
+    HostPool& pool = *dc.pool;
+    const phmm_batch& view = c.view;
+    const int g0 = c.g0, g1 = c.g1, n_regions = c.g1 - c.g0;
+    const int64_t out0 = c.out0;
+    const bool general = c.general;
+    const size_t o_read_off = c.o_read_off, o_hap_off = c.o_hap_off, o_reg_read = c.o_reg_read, o_reg_hap = c.o_reg_hap,
+                 o_reg_out = c.o_reg_out, o_bases = c.o_bases, o_q = c.o_q, o_gi = c.o_gi, o_gd = c.o_gd, o_gc = c.o_gc,
+                 o_haps = c.o_haps, in_bytes = c.in_bytes;
+    const auto t_begin = c.t_begin, t_packed = c.t_packed;
     // ---- phase B: plan on the packed copy, upload the jobs, launch ----
     Plan plan;
     {
@@ -865,6 +915,15 @@ int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1
                 ms(t_begin, t_packed), ms(t_packed, t_planned), ms(t_planned, t_end), p.n_jobs, p.launches, (long long)p.n_pairs);
     }
     return PHMM_OK;
+}
+
+// both phases in the calling thread (the staged form)
+int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1, int64_t out0,
+                     bool exact, bool do_launch, std::string& err)
+{
+    int rc = stage_pack(dc, s, b, g0, g1, out0, err);
+    if (rc) return rc;
+    return stage_launch(dc, s, exact, do_launch, err);
 }
 
 // Wait for the slot, fetch the rescue list if any, convert raw sums to log10 (intel_pairhmm.hpp:137-143).
@@ -1132,7 +1191,7 @@ int phmm_create(const phmm_options* opt, phmm_engine** out)
         if (rc) { fprintf(stderr, "phmm_create: %s\n", err.c_str()); return rc; }
         e->devs.push_back(std::move(dc));
     }
-    for (auto& dc : e->devs) { DeviceCtx* p = dc.get(); dc->worker = std::thread([p] { p->run(); }); }
+    for (auto& dc : e->devs) { dc->worker.start(dc->ordinal); dc->packer.start(dc->ordinal); }
     *out = e.release();
     return PHMM_OK;
 }
@@ -1141,9 +1200,8 @@ void phmm_destroy(phmm_engine* e)
 {
     if (!e) return;
     for (auto& dc : e->devs) {
-        { std::lock_guard<std::mutex> lk(dc->mu); dc->stop = true; }
-        dc->cv.notify_all();
-        if (dc->worker.joinable()) dc->worker.join();
+        dc->packer.finish();      // a pack task may still post its launch task to the worker: packer first
+        dc->worker.finish();
         cudaSetDevice(dc->ordinal);
         for (auto& s : dc->slots) { if (s.stream) cudaStreamSynchronize(s.stream); free_slot(s); }
         cudaFree(dc->d_ph2pr_f); cudaFree(dc->d_mm_f); cudaFree(dc->d_ph2pr_d); cudaFree(dc->d_mm_d);
@@ -1190,15 +1248,19 @@ int phmm_submit(phmm_engine* e, const phmm_batch* b, phmm_ticket* t)
         int* rc_out = &rcs[d];
         std::string* err_out = &errs[d];
         Latch* lp = &latch;
-        dc.post([=] {
-            // phase A of stage_and_launch ends with `copied`: from then on the submitter (and everything on
-            // its stack: rcs, errs, latch, the batch) is gone, and a failure is parked in the slot for phmm_wait
-            bool released = false;
+        dc.packer.post([=] {
+            // pack on the device's packer thread; then the submitter is released -- from there on everything on
+            // its stack (rcs, errs, latch, the batch) is gone -- and the plan + launch phase goes to the worker,
+            // where a failure is parked in the slot for phmm_wait
             std::string local_err;
-            const int rc = stage_and_launch(*dcp, *sp, b, g0, g1, out0, exact, true, local_err,
-                                            [&] { released = true; lp->done(); });
-            if (!released) { *rc_out = rc; *err_out = local_err; lp->done(); }
-            else if (rc) { sp->async_rc = rc; sp->async_err = local_err; }
+            const int rc = stage_pack(*dcp, *sp, b, g0, g1, out0, local_err);
+            if (rc) { *rc_out = rc; *err_out = local_err; lp->done(); return; }
+            dcp->post([=] {               // queued BEFORE the release: a phmm_wait that follows lands behind it
+                std::string e2;
+                const int rc2 = stage_launch(*dcp, *sp, exact, true, e2);
+                if (rc2) { sp->async_rc = rc2; sp->async_err = e2; }
+            });
+            lp->done();
         });
         rec.parts.emplace_back(d, slot_of[d]);
     }
