@@ -2,6 +2,7 @@
 // that carry the members the engine touches.  Prints the kept read indices and the matrix (%.17g) so
 // tests/test_cpp_mirror.py can compare it with the Python face and the golden fixtures.
 //   usage: host_mirror_main <region.txt>     lines: "H <bases>" | "R <seq> <qual>"
+//          host_mirror_main --sw <ref> <alt> [<alt> ...]      hc::B200SWAligner::align / align_batch: "offset cigar" lines
 //          host_mirror_main --batched <r1.txt> <r2.txt> ...   every region through hc::B200RegionBatcher (tiny
 //          flush threshold, so several asynchronous batches), taken in REVERSE order; prints "region <i>"
 //          before each region's block
@@ -13,6 +14,7 @@
 #include <vector>
 
 #include "b200_pairhmm.hpp"
+#include "b200_smithwaterman.hpp"
 
 struct Haplotype { std::string bases; };
 struct SAMRecord { std::string QNAME, SEQ, QUAL; std::size_t size() const { return SEQ.size(); } };
@@ -39,6 +41,23 @@ static void print(const std::vector<SAMRecord>& reads, const std::vector<std::ve
 int main(int argc, char** argv)
 {
     if (argc < 2) { std::fprintf(stderr, "usage: %s [--batched] region.txt ...\n", argv[0]); return 2; }
+    if (std::string(argv[1]) == "--sw") {             // host_mirror_main --sw <ref> <alt> [<alt> ...]: hc::B200SWAligner
+        try {
+            hc::B200SWAligner aligner;                 // assembler/graph_wrapper.hpp:232
+            std::vector<std::pair<std::string_view, std::string_view>> pairs;
+            for (int i = 3; i < argc; i++) pairs.emplace_back(argv[2], argv[i]);
+            if (pairs.size() == 1) {
+                auto [alignment_begin, cigar] = aligner.align(argv[2], argv[3]);       // :235
+                std::printf("%zu %s\n", alignment_begin, cigar.c_str());
+            } else {
+                for (auto& r : aligner.align_batch(pairs)) std::printf("%zu %s\n", r.first, r.second.c_str());
+            }
+        } catch (const std::exception& e) {
+            std::fprintf(stderr, "error: %s\n", e.what());
+            return 1;
+        }
+        return 0;
+    }
     if (std::string(argv[1]) == "--batched") {
         const int n = argc - 2;
         std::vector<std::vector<Haplotype>> haps(n);

@@ -85,3 +85,28 @@ def test_region_batcher_equals_per_region_calls(exe, tmp_path, golden):
     assert sorted(blocks) == list(range(len(paths)))
     for i in range(len(paths)):
         assert blocks[i] == single[i], f"region {i}"
+
+
+@pytest.mark.gpu
+def test_cpp_sw_aligner_mirror(exe, pkg):
+    """hc::B200SWAligner (include/b200_smithwaterman.hpp): align() and align_batch() give what the Python face
+    of phmm_sw_align gives (which tests/test_sw.py pins to the reference)."""
+    rng = np.random.default_rng(21)
+    alpha = np.frombuffer(b"ACGT", np.uint8)
+    ref = alpha[rng.integers(0, 4, 300)].tobytes().decode()
+    alts = [ref[20:200], ref[:100] + "ACGTAC" + ref[100:], ref[:150] + ref[161:], ref]
+    want, _ = pkg.sw_align([(ref.encode(), a.encode()) for a in alts])
+    r = subprocess.run([exe, "--sw", ref] + alts, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = [(int(ln.split()[0]), ln.split()[1]) for ln in r.stdout.strip().splitlines()]
+    assert got == want
+    r = subprocess.run([exe, "--sw", ref, alts[1]], capture_output=True, text=True)
+    assert r.returncode == 0 and (int(r.stdout.split()[0]), r.stdout.split()[1]) == want[1]
+
+
+def test_cpp_sw_aligner_fails_loudly_without_gpu(exe):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([exe, "--sw", "ACGTACGTAA", "ACGTTTACGTAA"], capture_output=True, text=True)
+    assert r.returncode == 1 and "no usable sm_100" in r.stderr
