@@ -53,7 +53,7 @@ class _Batch(C.Structure):
                 ("read_d", C.c_void_p), ("read_c", C.c_void_p), ("hap_off", C.c_void_p),
                 ("hap_bases", C.c_void_p),
                 ("gap_open_i", C.c_uint8), ("gap_open_d", C.c_uint8), ("gap_cont_c", C.c_uint8),
-                ("reserved0", C.c_uint8)]
+                ("flags", C.c_uint8)]
 
 
 class Stats(C.Structure):
@@ -73,7 +73,8 @@ class _Result(C.Structure):
 EXPORTS = ["phmm_create", "phmm_destroy", "phmm_compute", "phmm_submit", "phmm_wait", "phmm_strerror",
            "phmm_last_error", "phmm_abi_version", "phmm_normalize_filter", "phmm_tables",
            "phmm_stage", "phmm_run_staged", "phmm_run_staged_ex", "phmm_run_staged_pipelined",
-           "phmm_fetch_staged", "phmm_free_staged", "phmm_plan", "phmm_sw_align"]
+           "phmm_fetch_staged", "phmm_free_staged", "phmm_plan", "phmm_sw_align", "phmm_host_register",
+           "phmm_host_unregister"]
 
 class _PlanInfo(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("mode", C.c_int32), ("n_jobs", C.c_int32), ("n_long_pairs", C.c_int32),
@@ -154,6 +155,8 @@ def lib():
         L.phmm_run_staged_pipelined.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int32,
                                                 C.POINTER(C.c_float), C.POINTER(C.c_int32)]
         L.phmm_plan.argtypes = [C.POINTER(_Batch), C.c_int32, C.c_int32, C.POINTER(_PlanInfo), C.c_void_p, C.c_int64]
+        L.phmm_host_register.argtypes = [C.c_void_p, C.c_size_t]
+        L.phmm_host_unregister.argtypes = [C.c_void_p]
         L.phmm_sw_align.argtypes = [C.c_int32, C.POINTER(_SwBatch), C.POINTER(_SwResult)]
         L.phmm_fetch_staged.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_Result)]
         L.phmm_free_staged.argtypes = [C.c_void_p, C.c_void_p]; L.phmm_free_staged.restype = None
@@ -253,7 +256,29 @@ class Batch:
         else:
             b.read_i = b.read_d = b.read_c = None
         b.gap_open_i, b.gap_open_d, b.gap_cont_c = self.gap_open_i, self.gap_open_d, self.gap_cont_c
+        b.flags = 1 if getattr(self, "_pinned", False) else 0       # PHMM_BATCH_PINNED_INPUTS
         return b
+
+    def pin(self):
+        """Page-lock the byte arrays (phmm_host_register) and mark the batch PHMM_BATCH_PINNED_INPUTS: submits
+        then upload straight from these arrays (they must stay alive and unchanged until the matching wait)."""
+        if not getattr(self, "_pinned", False):
+            arrs = [self.read_bases, self.read_q, self.hap_bases] + ([self.read_i, self.read_d, self.read_c] if self.explicit_gaps else [])
+            for a in arrs:
+                if a.nbytes:
+                    rc = lib().phmm_host_register(a.ctypes.data_as(C.c_void_p), a.nbytes)
+                    if rc != PHMM_OK:
+                        raise PhmmError(rc, lib().phmm_strerror(rc).decode())
+            self._pinned_arrays = arrs
+            self._pinned = True
+        return self
+
+    def unpin(self):
+        if getattr(self, "_pinned", False):
+            for a in self._pinned_arrays:
+                if a.nbytes:
+                    lib().phmm_host_unregister(a.ctypes.data_as(C.c_void_p))
+            self._pinned = False
 
     @staticmethod
     def from_regions(regions, **kw):

@@ -240,6 +240,7 @@ struct Slot {
                o_gi = 0, o_gd = 0, o_gc = 0, o_haps = 0, in_bytes = 0;
         phmm_batch view{};                   // the part as a batch of its own, over the packed copy
         bool general = false, empty = true;
+        bool zero_copy = false;              // PHMM_BATCH_PINNED_INPUTS: byte arrays upload from the caller's memory
         int g0 = 0, g1 = 0;
         int64_t out0 = 0;
         std::chrono::steady_clock::time_point t_begin, t_packed;
@@ -741,6 +742,8 @@ int stage_pack(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1, int6
     uint8_t gap[3];
     const bool general = detect_gap_mode(b, rb0, rb1, gap) == kModeGeneral;
     c.general = general;
+    const bool zero_copy = (b->flags & PHMM_BATCH_PINNED_INPUTS) != 0;
+    c.zero_copy = zero_copy;
 
     // ---- phase A: layout of the data block, pack, upload ----
     size_t off = 0;
@@ -769,6 +772,7 @@ int stage_pack(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1, int6
         };
         pool.parallel_for(n_slices + 1, [&](int t) {
             if (t < n_slices) {
+                if (zero_copy) return;                      // uploaded straight from the caller's pinned arrays
                 slice_copy(o_bases, b->read_bases + rb0, read_bytes, t);
                 slice_copy(o_q, b->read_q + rb0, read_bytes, t);
                 if (general) {
@@ -807,16 +811,30 @@ int stage_pack(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1, int6
     view.region_read_beg = (const int32_t*)(hp + o_reg_read);
     view.region_hap_beg = (const int32_t*)(hp + o_reg_hap);
     view.read_off = (const int32_t*)(hp + o_read_off);
-    view.read_bases = hp + o_bases; view.read_q = hp + o_q;
-    view.read_i = general ? hp + o_gi : nullptr;
-    view.read_d = general ? hp + o_gd : nullptr;
-    view.read_c = general ? hp + o_gc : nullptr;
+    // (zero copy: the byte arrays stay the caller's, valid until phmm_wait by contract)
+    view.read_bases = zero_copy ? b->read_bases + rb0 : hp + o_bases;
+    view.read_q = zero_copy ? b->read_q + rb0 : hp + o_q;
+    view.read_i = !general ? nullptr : zero_copy ? b->read_i + rb0 : hp + o_gi;
+    view.read_d = !general ? nullptr : zero_copy ? b->read_d + rb0 : hp + o_gd;
+    view.read_c = !general ? nullptr : zero_copy ? b->read_c + rb0 : hp + o_gc;
     view.hap_off = (const int32_t*)(hp + o_hap_off);
-    view.hap_bases = hp + o_haps;
+    view.hap_bases = zero_copy ? b->hap_bases + hb0 : hp + o_haps;
     view.gap_open_i = gap[0]; view.gap_open_d = gap[1]; view.gap_cont_c = gap[2];
     c.t_packed = std::chrono::steady_clock::now();
-    CUDA_TRY(cudaMemcpyAsync(s.d_in.p, s.h_in.p, in_bytes, cudaMemcpyHostToDevice, s.stream));
-    return PHMM_OK;                       // the submitter's arrays are no longer needed
+    if (!zero_copy) CUDA_TRY(cudaMemcpyAsync(s.d_in.p, s.h_in.p, in_bytes, cudaMemcpyHostToDevice, s.stream));
+    else {
+        uint8_t* dpz = (uint8_t*)s.d_in.p;
+        CUDA_TRY(cudaMemcpyAsync(dpz, hp, o_bases, cudaMemcpyHostToDevice, s.stream));          // the index arrays
+        CUDA_TRY(cudaMemcpyAsync(dpz + o_bases, b->read_bases + rb0, read_bytes, cudaMemcpyHostToDevice, s.stream));
+        CUDA_TRY(cudaMemcpyAsync(dpz + o_q, b->read_q + rb0, read_bytes, cudaMemcpyHostToDevice, s.stream));
+        if (general) {
+            CUDA_TRY(cudaMemcpyAsync(dpz + o_gi, b->read_i + rb0, read_bytes, cudaMemcpyHostToDevice, s.stream));
+            CUDA_TRY(cudaMemcpyAsync(dpz + o_gd, b->read_d + rb0, read_bytes, cudaMemcpyHostToDevice, s.stream));
+            CUDA_TRY(cudaMemcpyAsync(dpz + o_gc, b->read_c + rb0, read_bytes, cudaMemcpyHostToDevice, s.stream));
+        }
+        CUDA_TRY(cudaMemcpyAsync(dpz + o_haps, b->hap_bases + hb0, hap_bytes, cudaMemcpyHostToDevice, s.stream));
+    }
+    return PHMM_OK;                       // the submitter's arrays are no longer needed (zero copy: only the index arrays)
 }
 
 int stage_launch(DeviceCtx& dc, Slot& s, bool exact, bool do_launch, std::string& err)
@@ -1131,6 +1149,18 @@ int phmm_normalize_filter(double* lik, int32_t n_reads, int32_t n_haps, const in
         kept += keep[i];
     }
     return kept;
+}
+
+int phmm_host_register(void* p, size_t bytes)
+{
+    if (!p || !bytes) return PHMM_ERR_INVALID_ARG;
+    return cudaHostRegister(p, bytes, cudaHostRegisterPortable) == cudaSuccess ? PHMM_OK : PHMM_ERR_CUDA;
+}
+
+int phmm_host_unregister(void* p)
+{
+    if (!p) return PHMM_ERR_INVALID_ARG;
+    return cudaHostUnregister(p) == cudaSuccess ? PHMM_OK : PHMM_ERR_CUDA;
 }
 
 int phmm_plan(const phmm_batch* b, int32_t sm_count, int32_t host_threads, phmm_plan_info* info,

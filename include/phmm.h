@@ -100,8 +100,18 @@ typedef struct phmm_batch {
     const uint8_t* read_c;            /* gap continuation, per base, or NULL   */
     const int32_t* hap_off;           /* [n_haps+1]    */
     const uint8_t* hap_bases;
-    uint8_t gap_open_i, gap_open_d, gap_cont_c, reserved0;   /* used when read_i == NULL */
+    uint8_t gap_open_i, gap_open_d, gap_cont_c;               /* used when read_i == NULL */
+    uint8_t flags;                                           /* PHMM_BATCH_* */
 } phmm_batch;
+
+/* phmm_batch.flags.  PINNED_INPUTS: read_bases, read_q, (read_i, read_d, read_c) and hap_bases are page-locked
+ * (cudaMallocHost / cudaHostRegister, e.g. phmm_host_register below) and stay valid and unchanged until
+ * phmm_wait returns: the engine then uploads them straight from the caller's memory instead of copying them
+ * into its own pinned staging first (the index arrays are still copied and may be released at once).  Worth
+ * it for read-heavy streams on many GPUs, where that copy is the host-memory-bandwidth limit. */
+#define PHMM_BATCH_PINNED_INPUTS 1
+int  phmm_host_register(void* p, size_t bytes);      /* cudaHostRegister / cudaHostUnregister for callers   */
+int  phmm_host_unregister(void* p);                  /* without a CUDA toolchain of their own               */
 
 typedef struct phmm_stats {
     int64_t n_pairs, n_cells, n_rescued;

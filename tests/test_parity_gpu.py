@@ -274,6 +274,26 @@ def test_submit_wait_pipeline_and_staged_path(pkg, engine, oracle):
     assert np.array_equal(res.log10.view(np.uint64), sync[2].view(np.uint64))
 
 
+def test_pinned_inputs_upload_without_the_staging_copy(pkg, engine):
+    """PHMM_BATCH_PINNED_INPUTS: the byte arrays go to the device straight from the caller's page-locked memory;
+    same bits as the staged-copy path, through compute and through several tickets in flight, with constant
+    and with per-base gap penalties."""
+    for b in (pkg.synth.s3(3), pkg.synth.random_small(5, n_regions=9, max_reads=30, max_haps=6),
+              next(pkg.synth.s5_stream(64, windows_per_batch=64))):
+        want = engine.compute(b)
+        b.pin()
+        try:
+            got = engine.compute(b)
+            assert np.array_equal(got.log10.view(np.uint64), want.log10.view(np.uint64))
+            assert np.array_equal(got.rescued, want.rescued)
+            tickets = [engine.submit(b) for _ in range(2)]
+            for t in tickets:
+                assert np.array_equal(engine.wait(t).log10.view(np.uint64), want.log10.view(np.uint64))
+        finally:
+            b.unpin()
+        assert np.array_equal(engine.compute(b).log10.view(np.uint64), want.log10.view(np.uint64))
+
+
 def test_edge_cases_and_errors(pkg, engine, oracle):
     B = pkg.Batch
     # regions without reads or without haplotypes contribute no pairs; empty batch is fine

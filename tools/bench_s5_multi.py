@@ -13,8 +13,11 @@ n_win = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 wpb = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 1      # the distinct batches are streamed `reps` times over
 batches = list(pkg.synth.s5_stream(n_win, windows_per_batch=wpb)) * reps
+pinned = len(sys.argv) > 4 and sys.argv[4] == "pinned"     # PHMM_BATCH_PINNED_INPUTS: no staging copy of the byte arrays
+if pinned:
+    for b in {id(x): x for x in batches}.values(): b.pin()
 cells = sum(b.n_cells for b in batches)
-out = {"windows": n_win * reps, "distinct_windows": n_win, "windows_per_batch": wpb, "batches": len(batches), "cells": int(cells),
+out = {"pinned_inputs": pinned, "windows": n_win * reps, "distinct_windows": n_win, "windows_per_batch": wpb, "batches": len(batches), "cells": int(cells),
        "pairs": int(sum(b.n_pairs for b in batches)), "host_cores": os.cpu_count(), "rows": []}
 for n in (1, 2, 4, 8):
     if n > torch.cuda.device_count(): break
