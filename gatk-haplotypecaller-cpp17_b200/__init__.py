@@ -43,7 +43,7 @@ def build(verbose=False):
 class _Options(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("n_devices", C.c_int32), ("devices", C.POINTER(C.c_int32)),
                 ("pipeline_depth", C.c_int32), ("exact_fp32", C.c_int32), ("host_threads", C.c_int32),
-                ("reserved", C.c_int32 * 3)]
+                ("use_double", C.c_int32), ("fp64_first", C.c_int32), ("reserved", C.c_int32 * 1)]
 
 
 class _Batch(C.Structure):
@@ -74,7 +74,7 @@ EXPORTS = ["phmm_create", "phmm_destroy", "phmm_compute", "phmm_submit", "phmm_w
            "phmm_last_error", "phmm_abi_version", "phmm_normalize_filter", "phmm_tables",
            "phmm_stage", "phmm_run_staged", "phmm_run_staged_ex", "phmm_run_staged_pipelined",
            "phmm_fetch_staged", "phmm_free_staged", "phmm_plan", "phmm_sw_align", "phmm_host_register",
-           "phmm_host_unregister"]
+           "phmm_host_unregister", "phmm_host_alloc", "phmm_host_free"]
 
 class _PlanInfo(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("mode", C.c_int32), ("n_jobs", C.c_int32), ("n_long_pairs", C.c_int32),
@@ -157,6 +157,8 @@ def lib():
         L.phmm_plan.argtypes = [C.POINTER(_Batch), C.c_int32, C.c_int32, C.POINTER(_PlanInfo), C.c_void_p, C.c_int64]
         L.phmm_host_register.argtypes = [C.c_void_p, C.c_size_t]
         L.phmm_host_unregister.argtypes = [C.c_void_p]
+        L.phmm_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+        L.phmm_host_free.argtypes = [C.c_void_p]
         L.phmm_sw_align.argtypes = [C.c_int32, C.POINTER(_SwBatch), C.POINTER(_SwResult)]
         L.phmm_fetch_staged.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_Result)]
         L.phmm_free_staged.argtypes = [C.c_void_p, C.c_void_p]; L.phmm_free_staged.restype = None
@@ -244,6 +246,27 @@ class Batch:
                      self.read_off[r0:r1 + 1] - b0, self.read_bases[b0:b1], self.read_q[b0:b1],
                      self.hap_off[h0:h1 + 1] - c0, self.hap_bases[c0:c1], **kw)
 
+    @staticmethod
+    def concat(batches):
+        """Several batches as one (regions in order)."""
+        batches = list(batches)
+        if len(batches) == 1:
+            return batches[0]
+        b0 = batches[0]
+        assert all(b.explicit_gaps == b0.explicit_gaps for b in batches)
+        def offs(name):
+            out, base = [np.zeros(1, np.int64)], 0
+            for b in batches:
+                a = np.asarray(getattr(b, name), np.int64)
+                out.append(a[1:] + base); base += int(a[-1])
+            return np.concatenate(out)
+        cat = lambda name: np.concatenate([getattr(b, name) for b in batches])
+        kw = dict(gap_open_i=b0.gap_open_i, gap_open_d=b0.gap_open_d, gap_cont_c=b0.gap_cont_c)
+        if b0.explicit_gaps:
+            kw.update(read_i=cat("read_i"), read_d=cat("read_d"), read_c=cat("read_c"))
+        return Batch(offs("region_read_beg"), offs("region_hap_beg"), offs("read_off"), cat("read_bases"), cat("read_q"),
+                     offs("hap_off"), cat("hap_bases"), **kw)
+
     def c_struct(self):
         p = lambda a: a.ctypes.data_as(C.c_void_p)
         b = _Batch()
@@ -264,21 +287,31 @@ class Batch:
         then upload straight from these arrays (they must stay alive and unchanged until the matching wait)."""
         if not getattr(self, "_pinned", False):
             arrs = [self.read_bases, self.read_q, self.hap_bases] + ([self.read_i, self.read_d, self.read_c] if self.explicit_gaps else [])
+            self._pinned_arrays = []                     # every successful registration is recorded as it happens
             for a in arrs:
                 if a.nbytes:
                     rc = lib().phmm_host_register(a.ctypes.data_as(C.c_void_p), a.nbytes)
                     if rc != PHMM_OK:
+                        self._unregister_all()           # roll back: nothing stays page-locked behind a failed pin()
                         raise PhmmError(rc, lib().phmm_strerror(rc).decode())
-            self._pinned_arrays = arrs
+                    self._pinned_arrays.append(a)
             self._pinned = True
         return self
 
+    def _unregister_all(self):
+        for a in getattr(self, "_pinned_arrays", []):
+            lib().phmm_host_unregister(a.ctypes.data_as(C.c_void_p))
+        self._pinned_arrays = []
+
     def unpin(self):
-        if getattr(self, "_pinned", False):
-            for a in self._pinned_arrays:
-                if a.nbytes:
-                    lib().phmm_host_unregister(a.ctypes.data_as(C.c_void_p))
-            self._pinned = False
+        self._unregister_all()
+        self._pinned = False
+
+    def __del__(self):                                   # never free memory that is still cudaHostRegister-ed
+        try:
+            self._unregister_all()
+        except Exception:
+            pass
 
     @staticmethod
     def from_regions(regions, **kw):
@@ -344,7 +377,7 @@ class Result:
 class PairHMMEngine:
     """Owns one phmm_engine (streams, memory pool, worker per device)."""
 
-    def __init__(self, devices=None, pipeline_depth=2, exact_fp32=False, host_threads=1):
+    def __init__(self, devices=None, pipeline_depth=2, exact_fp32=False, host_threads=1, use_double=False, fp64_first=0):
         self._L = lib()
         opt = _Options()
         opt.struct_size = C.sizeof(_Options)
@@ -353,6 +386,8 @@ class PairHMMEngine:
         opt.n_devices = len(devices)
         opt.devices = C.cast(self._dev_arr, C.POINTER(C.c_int32))
         opt.pipeline_depth, opt.exact_fp32, opt.host_threads = pipeline_depth, int(exact_fp32), host_threads
+        opt.fp64_first = int(fp64_first)                # 0 auto, 1 never, 2 always (include/phmm.h)
+        opt.use_double = int(use_double)                # the reference's g_use_double (intel_pairhmm.hpp:58,71,135)
         self._h = C.c_void_p()
         rc = self._L.phmm_create(C.byref(opt), C.byref(self._h))
         if rc != PHMM_OK:

@@ -45,7 +45,7 @@ constexpr int kPerHapTableBytes = 8 + 4 + 4 + 4;     // init_y, haplotype index,
 inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 
 struct KernelTable {
-    // [f64][exact] -> [mode][aligned][shape]
+    // [f64][exact] -> [mode][aligned][shape][list]
     KernelTab fn[2][2];
     KernelTable() {
         register_f32_fast(fn[0][0]);
@@ -216,6 +216,7 @@ struct Part {
     int job_beg[2 * kNumShapes + 1] = {0};  // jobs are grouped by kernel slot = shape + kNumShapes * aligned
     int haps_per_job = 1, hap_chunks = 1;
     int haps_per_job64 = 1, hap_chunks64 = 1;    // chunking of the FP64 redo launches (see stage_and_launch)
+    bool f64_first = false;                  // FP64-first order (launch_kernels): the previous batch was rescue-dense
     size_t h2d_bytes = 0, d2h_bytes = 0;
     int launches = 0;
     float kernel_ms = 0.f;
@@ -232,7 +233,8 @@ struct Slot {
     cudaEvent_t ev_k32 = nullptr;            // after the FP32 launch of a single-shape batch (dominant-kernel timing)
     bool k32_valid = false;
     PinnedBuf h_in, h_jobs, h_out, h_rescue;
-    DeviceBuf d_in, d_jobs, d_out, d_rescue, d_flags;
+    DeviceBuf d_in, d_jobs, d_out, d_rescue, d_flags, d_work;
+    int sm_count = 148;
     int async_rc = PHMM_OK;                  // failure after the submitter was released: reported by phmm_wait
     std::string async_err;
     struct StageCtx {                        // what the pack phase hands to the plan + launch phase
@@ -257,6 +259,7 @@ struct DeviceCtx {
     int ordinal = 0;
     int sm_count = 148;
     float last_rescue_frac = 0.f;        // share of pairs the previous batch redid in FP64
+    int fp64_first_opt = 0;              // phmm_options.fp64_first
     std::unique_ptr<HostPool> pool;      // host_threads - 1 helpers for this device's worker thread
     std::vector<Slot> slots;
     int next_slot = 0;
@@ -335,6 +338,14 @@ struct phmm_staged {
 
 namespace {
 
+// Public entry points leave the calling thread's current CUDA device as they found it (a caller that also
+// drives torch / its own CUDA code must not be redirected by a library call).
+struct DeviceGuard {
+    int saved = -1;
+    DeviceGuard() { if (cudaGetDevice(&saved) != cudaSuccess) saved = -1; }
+    ~DeviceGuard() { if (saved >= 0) cudaSetDevice(saved); }
+};
+
 #define CUDA_TRY(expr)                                                                            \
     do {                                                                                          \
         cudaError_t e__ = (expr);                                                                 \
@@ -395,21 +406,67 @@ int64_t region_cells(const phmm_batch* b, int g)
     return (int64_t)(b->read_off[r1] - b->read_off[r0]) * (b->hap_off[h1] - b->hap_off[h0]);
 }
 
+// The units (job, chunk) whose flag byte carries `bit`, as work items for a LIST launch: every such unit is cut
+// into `subs` pieces of the consumer's haps_per_job.  One thread per unit of the launch slot.
+__global__ void build_work_list(const uint8_t* __restrict__ flags, const int n_units, const unsigned bit, const int subs,
+                                uint2* __restrict__ list, unsigned* __restrict__ count)
+{
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_units || !(flags[u] & bit)) return;
+    const unsigned at = atomicAdd(count, (unsigned)subs);
+    for (int s = 0; s < subs; ++s) list[at + s] = make_uint2((unsigned)u, (unsigned)s);
+}
+
+// Resident warps per SM of a kernel at a given dynamic shared memory size (persistent work-list launches are
+// sized to fill the chip once); cached, the occupancy query is not free.
+int resident_ctas_per_sm(KernelFn fn, size_t smem)
+{
+    static std::mutex mu;
+    static std::map<std::pair<const void*, size_t>, int> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    auto key = std::make_pair((const void*)fn, smem);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, (const void*)fn, kWarpsPerCta * 32, smem) != cudaSuccess || n < 1) {
+        cudaGetLastError();
+        n = 8;
+    }
+    cache[key] = n;
+    return n;
+}
+
+// Header of the flags buffer: per kernel slot k four counters {count, cursor} of the FP64 work list (filled by
+// the FP32 launch) and {count, cursor} of the FP32 work list (filled by an FP64-first launch).
+constexpr size_t kWorkHeaderBytes = ((size_t)2 * kNumShapes * 4 * sizeof(unsigned) + 255) / 256 * 256;
+
 // Forward (FP32) and rescue (FP64) kernels of a staged slot.  Every kernel slot (shape x aligned) is an
-// independent launch pair; they are spread over a few auxiliary streams forked from / joined to the
+// independent chain of launches; the chains are spread over a few auxiliary streams forked from / joined to the
 // slot's stream so that the small grids of a ragged batch overlap.  ev_k0 / ev_k1 bracket the lot.
-// Precision tiers [tier_lo, tier_hi] (phmm_kernels.cuh): 1 FP32, 2 its FP64 redo, 3 the flush-exact FP64
-// redo of pairs that ended within reach of the denormal range.  The normal pass is tiers 1-2; tier 3 is
-// launched by finalize_part only when the downloaded results show a marked pair (pathological inputs).
-int launch_kernels(Slot& s, bool exact, int tier_lo, int tier_hi, std::string& err)
+// Precision tiers (phmm_kernels.cuh): 1 FP32, 2 its FP64 redo, 3 the flush-exact FP64 redo of pairs that ended
+// within reach of the denormal range, 0 the FP64-first pass.  Three orders for the normal pass [1, 2]:
+//   FP32 first (default)   FP32 over the grid -> FP64 redo PULLING the (job, haplotype) units the FP32 launch
+//                          listed (empty list: the launch is a few idle warps);
+//   FP64 first (p.f64_first: the device's previous batch redid most of its pairs)
+//                          FP64 over the grid -> FP32 only for the units holding a pair that may not underflow ->
+//                          FP64 redo of what that FP32 pass still underflowed; see kCertainUnderflow64;
+//   use_double             FP64 over the grid with every flag raised (intel_pairhmm.hpp:135).
+// Tier 3 is launched by finalize_part only when the downloaded results show a marked pair (pathological inputs).
+int launch_kernels(Slot& s, bool exact, int tier_lo, int tier_hi, std::string& err, bool use_double = false)
 {
     Part& p = s.part;
     const KernelArgs& a = s.args;
-    if (tier_lo == 1) {
+    const bool normal_pass = tier_lo == 1;
+    const bool skip32 = use_double && normal_pass;
+    const bool f64_first = p.f64_first && normal_pass && !skip32 && !exact;   // (exact: raw FP32 sums are an output)
+    uint8_t* const flags_base = (uint8_t*)s.d_flags.p;
+    unsigned* const counters = (unsigned*)flags_base;
+    if (normal_pass) {
         p.launches = 0;
         s.k32_valid = false;
-        CUDA_TRY(cudaMemsetAsync(s.d_out.p, 0, 16, s.stream));
-        CUDA_TRY(cudaMemsetAsync(s.d_flags.p, 0, (size_t)p.n_jobs * p.hap_chunks, s.stream));
+        CUDA_TRY(cudaMemsetAsync(s.d_out.p, 0, skip32 ? 16 + sizeof(float) * (size_t)p.n_pairs : 16, s.stream));
+        CUDA_TRY(cudaMemsetAsync(flags_base, 0, kWorkHeaderBytes, s.stream));
+        CUDA_TRY(cudaMemsetAsync(flags_base + kWorkHeaderBytes, skip32 ? 1 : 0, (size_t)p.n_jobs * p.hap_chunks, s.stream));
         CUDA_TRY(cudaEventRecord(s.ev_k0, s.stream));
     }
     int n_kernels = 0;
@@ -418,6 +475,8 @@ int launch_kernels(Slot& s, bool exact, int tier_lo, int tier_hi, std::string& e
     bool used[kAuxStreams] = {false, false, false, false};
     if (fork) CUDA_TRY(cudaEventRecord(s.ev_fork, s.stream));
     int which = 0;
+    const int subs64 = (p.haps_per_job + p.haps_per_job64 - 1) / p.haps_per_job64;    // FP64 items per FP32 unit
+    size_t work_off = 0;                                     // in uint2 items: every slot owns [FP64 list | FP32 list]
     for (int k = 0; k < 2 * kNumShapes; k++) {
         const int n = p.job_beg[k + 1] - p.job_beg[k];
         if (n == 0) continue;
@@ -429,24 +488,62 @@ int launch_kernels(Slot& s, bool exact, int tier_lo, int tier_hi, std::string& e
         }
         const int per_warp = smem_bytes_per_warp(a.stream_cap, p.haps_per_job, kShapes[k % kNumShapes]);
         const size_t smem = (size_t)per_warp * kWarpsPerCta;
+        const size_t cap64 = (size_t)n * p.hap_chunks * subs64, cap32 = (size_t)n * p.hap_chunks;
+        uint2* const list64 = (uint2*)s.d_work.p + work_off;
+        uint2* const list32 = list64 + cap64;
+        work_off += cap64 + cap32;
+        unsigned* const cnt = counters + 4 * k;              // {count64, cursor64, count32, cursor32}
         KernelArgs ak = a;
         ak.jobs = a.jobs + p.job_beg[k];
         ak.n_jobs = n;
         ak.job_flag_base = p.job_beg[k];
+        ak.job_flags = flags_base + kWorkHeaderBytes;
         ak.smem_bytes_per_warp = per_warp;
         ak.flag_hpj = p.haps_per_job;
         ak.flag_chunks = p.hap_chunks;
-        for (int tier = tier_lo; tier <= tier_hi; tier++) {       // tier 3 runs the EXACT FP64 kernel
-            ak.haps_per_job = tier == 1 ? p.haps_per_job : p.haps_per_job64;
-            dim3 grid((n + kWarpsPerCta - 1) / kWarpsPerCta, tier == 1 ? p.hap_chunks : p.hap_chunks64);
-            KernelFn fn = kernel_table().fn[tier >= 2][(exact || tier == 3) ? 1 : 0][p.mode][k / kNumShapes][k % kNumShapes];
-            ak.tier = tier;
+        // one launch of the chain: `tier`, walking the grid or (from_list) pulling the units whose flag carries
+        // `bit` from a list that build_work_list() compacts first
+        auto launch = [&](int tier, int hpj, int chunks, bool from_list, unsigned bit, uint2* list, unsigned* cnt_cur, size_t cap) -> int {
+            KernelArgs al = ak;
+            al.tier = tier;
+            al.haps_per_job = hpj;
+            al.first64 = f64_first ? 1 : 0;
+            KernelFn fn = kernel_table().fn[tier != 1][(exact || tier == 3) ? 1 : 0][p.mode][k / kNumShapes][k % kNumShapes][from_list ? 1 : 0];
+            if (!fn) { err = "kernel variant not compiled"; return PHMM_ERR_UNSUPPORTED; }
             if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            fn<<<grid, kWarpsPerCta * 32, smem, st>>>(ak);
+            dim3 grid((n + kWarpsPerCta - 1) / kWarpsPerCta, chunks);
+            if (from_list) {
+                const int n_units = n * p.hap_chunks, subs = (p.haps_per_job + hpj - 1) / hpj;
+                build_work_list<<<(n_units + 255) / 256, 256, 0, st>>>(ak.job_flags + (size_t)ak.job_flag_base * ak.flag_chunks, n_units,
+                                                                        bit, subs, list, cnt_cur);
+                CUDA_TRY(cudaGetLastError());
+                p.launches++;
+                al.work_in = list; al.work_in_count = cnt_cur; al.work_in_cursor = cnt_cur + 1;
+                const size_t fill = (size_t)s.sm_count * resident_ctas_per_sm(fn, smem);
+                grid = dim3((unsigned)std::max<size_t>(1, std::min(fill, cap)), 1);
+            }
+            fn<<<grid, kWarpsPerCta * 32, smem, st>>>(al);
             CUDA_TRY(cudaGetLastError());
             p.launches++;
-            if (tier == 1 && !fork) { CUDA_TRY(cudaEventRecord(s.ev_k32, st)); s.k32_valid = true; }
+            return PHMM_OK;
+        };
+        const bool lists = !exact;                           // the exact engines walk the grid (no LIST kernels compiled)
+        int rc = PHMM_OK;
+        if (!normal_pass) {                                  // tier 3 (or an explicit tier range): grid walks
+            for (int tier = tier_lo; tier <= tier_hi && !rc; tier++)
+                rc = launch(tier, tier == 1 ? p.haps_per_job : p.haps_per_job64, tier == 1 ? p.hap_chunks : p.hap_chunks64, false, 0, nullptr, nullptr, 0);
+        } else if (skip32) {
+            rc = launch(2, p.haps_per_job64, p.hap_chunks64, false, 0, nullptr, nullptr, 0);
+        } else if (f64_first) {
+            rc = launch(0, p.haps_per_job, p.hap_chunks, false, 0, nullptr, nullptr, 0);
+            if (!rc) rc = launch(1, p.haps_per_job, p.hap_chunks, true, kFlagNeedsF32, list32, cnt + 2, cap32);
+            if (!rc && tier_hi >= 2) rc = launch(2, p.haps_per_job64, p.hap_chunks64, true, kFlagRedo64, list64, cnt, cap64);
+        } else {
+            rc = launch(1, p.haps_per_job, p.hap_chunks, false, 0, nullptr, nullptr, 0);
+            if (!rc && !fork) { CUDA_TRY(cudaEventRecord(s.ev_k32, st)); s.k32_valid = true; }
+            if (!rc && tier_hi >= 2) rc = launch(2, p.haps_per_job64, p.hap_chunks64, lists, kFlagRedo64, list64, cnt, cap64);
         }
+        if (rc) return rc;
     }
     if (fork)
         for (int ai = 0; ai < kAuxStreams; ai++)
@@ -454,9 +551,9 @@ int launch_kernels(Slot& s, bool exact, int tier_lo, int tier_hi, std::string& e
                 CUDA_TRY(cudaEventRecord(s.ev_join[ai], s.aux[ai]));
                 CUDA_TRY(cudaStreamWaitEvent(s.stream, s.ev_join[ai], 0));
             }
-    if (tier_lo == 1) {
+    if (normal_pass) {
         if (p.n_long) {      // reads beyond one lane-group pass: all precision tiers inside one launch
-            launch_long_reads(a, s.d_long, p.n_long, p.mode == kModeGeneral, exact, s.stream);
+            launch_long_reads(a, s.d_long, p.n_long, p.mode == kModeGeneral, exact, use_double, s.stream);
             CUDA_TRY(cudaGetLastError());
             p.launches++;
         }
@@ -495,7 +592,7 @@ struct Plan {
 // Pure host logic, no CUDA call: fills `p` (counts, mode, job ranges per slot, chunking) and `plan` for
 // regions [g0, g1) of the batch.  Exported for tests and diagnostics as phmm_plan().
 int plan_part(const phmm_batch* b, int g0, int g1, int64_t out0, int sm_count, float last_rescue_frac,
-              HostPool& pool, Part& p, Plan& plan, std::string& err)
+              HostPool& pool, Part& p, Plan& plan, std::string& err, int fp64_first_opt = 0)
 {
     (void)err;
     static const bool trace_plan = getenv("PHMM_TRACE_PLAN") != nullptr;
@@ -693,6 +790,9 @@ int plan_part(const phmm_batch* b, int g0, int g1, int64_t out0, int sm_count, f
         const bool dense = last_rescue_frac > 0.05f;
         p.haps_per_job64 = dense ? hpj : 1;
         p.hap_chunks64 = (nhm + p.haps_per_job64 - 1) / p.haps_per_job64;
+        // FP64 first pays when more than 2/3 of the pairs end up in FP64 anyway (cost 2 + (1 - x) against 1 + 2x
+        // FP32-cell units for a redo share x); phmm_options.fp64_first: 0 auto, 1 never, 2 always
+        p.f64_first = fp64_first_opt == 1 ? false : fp64_first_opt == 2 ? true : last_rescue_frac > 0.75f;
     }
     if (trace_plan) {
         const auto tp3 = std::chrono::steady_clock::now();
@@ -729,6 +829,12 @@ int stage_pack(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1, int6
     p.g0 = g0; p.g1 = g1; p.out0 = out0;
     p.n_regions = g1 - g0;
     HostPool& pool = *dc.pool;
+    {   // test hook (tests/test_multi_device_gpu.py): PHMM_FAULT_PACK=<first region> makes the pack phase of the
+        // share that starts at that region fail ONCE, to exercise the partial-failure path of phmm_submit
+        static std::atomic<int> fault_at{[] { const char* v = getenv("PHMM_FAULT_PACK"); return v ? atoi(v) : -1; }()};
+        int want = g0;
+        if (g0 > 0 && fault_at.compare_exchange_strong(want, -1)) { err = "injected pack failure (PHMM_FAULT_PACK)"; return PHMM_ERR_CUDA; }
+    }
     const int r0 = b->region_read_beg[g0], r1 = b->region_read_beg[g1];
     const int h0 = b->region_hap_beg[g0], h1 = b->region_hap_beg[g1];
     const int n_reads = r1 - r0, n_haps = h1 - h0, n_regions = g1 - g0;
@@ -837,7 +943,7 @@ int stage_pack(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1, int6
     return PHMM_OK;                       // the submitter's arrays are no longer needed (zero copy: only the index arrays)
 }
 
-int stage_launch(DeviceCtx& dc, Slot& s, bool exact, bool do_launch, std::string& err)
+int stage_launch(DeviceCtx& dc, Slot& s, bool exact, bool use_double, bool do_launch, std::string& err)
 {
     static const bool trace = getenv("PHMM_TRACE") != nullptr;      // development aid: host time per phase
     Slot::StageCtx& c = s.stage;
@@ -855,7 +961,7 @@ int stage_launch(DeviceCtx& dc, Slot& s, bool exact, bool do_launch, std::string
     // ---- phase B: plan on the packed copy, upload the jobs, launch ----
     Plan plan;
     {
-        int rcp = plan_part(&view, 0, n_regions, out0, dc.sm_count, dc.last_rescue_frac, pool, p, plan, err);
+        int rcp = plan_part(&view, 0, n_regions, out0, dc.sm_count, dc.last_rescue_frac, pool, p, plan, err, dc.fp64_first_opt);
         if (rcp) return rcp;
         p.g0 = g0; p.g1 = g1; p.out0 = out0;
     }
@@ -871,7 +977,12 @@ int stage_launch(DeviceCtx& dc, Slot& s, bool exact, bool do_launch, std::string
     CUDA_TRY(s.h_out.reserve(out_bytes));
     CUDA_TRY(s.d_out.reserve(out_bytes));
     CUDA_TRY(s.d_rescue.reserve(sizeof(RescueOut) * (size_t)p.n_pairs));
-    CUDA_TRY(s.d_flags.reserve((size_t)p.n_jobs * p.hap_chunks + 16));
+    CUDA_TRY(s.d_flags.reserve(kWorkHeaderBytes + (size_t)p.n_jobs * p.hap_chunks + 16));
+    {   // work lists: per job and FP32 chunk one FP32 item and ceil(hpj / hpj64) FP64 items (launch_kernels)
+        const size_t subs64 = (size_t)(p.haps_per_job + p.haps_per_job64 - 1) / p.haps_per_job64;
+        CUDA_TRY(s.d_work.reserve(sizeof(uint2) * ((size_t)p.n_jobs * p.hap_chunks * (subs64 + 1) + 16)));
+    }
+    s.sm_count = dc.sm_count;
     {
         uint8_t* hj = (uint8_t*)s.h_jobs.p;
         if (!long_pairs.empty()) std::memcpy(hj + o_long, long_pairs.data(), sizeof(LongPair) * long_pairs.size());
@@ -914,14 +1025,15 @@ int stage_launch(DeviceCtx& dc, Slot& s, bool exact, bool do_launch, std::string
     a.rescue_count = (unsigned*)s.d_out.p;
     a.raw32 = (float*)((uint8_t*)s.d_out.p + 16);
     a.rescue_out = (RescueOut*)s.d_rescue.p;
-    a.job_flags = (uint8_t*)s.d_flags.p;
+    a.job_flags = (uint8_t*)s.d_flags.p + kWorkHeaderBytes;
     a.job_flag_base = 0;
+    a.work_in = nullptr; a.work_in_count = nullptr; a.work_in_cursor = nullptr; a.first64 = 0;
 
     if (jobs_bytes) CUDA_TRY(cudaMemcpyAsync(s.d_jobs.p, s.h_jobs.p, jobs_bytes, cudaMemcpyHostToDevice, s.stream));
     p.h2d_bytes = in_bytes + jobs_bytes;
     if (!do_launch) return PHMM_OK;
 
-    int rc = launch_kernels(s, exact, 1, 2, err);
+    int rc = launch_kernels(s, exact, 1, 2, err, use_double);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(s.h_out.p, s.d_out.p, out_bytes, cudaMemcpyDeviceToHost, s.stream));
     CUDA_TRY(cudaEventRecord(s.ev_done, s.stream));
@@ -937,11 +1049,11 @@ int stage_launch(DeviceCtx& dc, Slot& s, bool exact, bool do_launch, std::string
 
 // both phases in the calling thread (the staged form)
 int stage_and_launch(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1, int64_t out0,
-                     bool exact, bool do_launch, std::string& err)
+                     bool exact, bool use_double, bool do_launch, std::string& err)
 {
     int rc = stage_pack(dc, s, b, g0, g1, out0, err);
     if (rc) return rc;
-    return stage_launch(dc, s, exact, do_launch, err);
+    return stage_launch(dc, s, exact, use_double, do_launch, err);
 }
 
 // Wait for the slot, fetch the rescue list if any, convert raw sums to log10 (intel_pairhmm.hpp:137-143).
@@ -966,21 +1078,23 @@ int finalize_part(phmm_engine* e, DeviceCtx& dc, Slot& s, phmm_result* r, std::s
     double* o64 = r->raw64 ? r->raw64 + p.out0 : nullptr;
     uint8_t* ores = r->rescued ? r->rescued + p.out0 : nullptr;
     const float log10_init_f = T.log10_init_f;
-    std::atomic<int64_t> need_rescue{0}, marked{0};
+    std::atomic<int64_t> need_rescue{0}, marked{0}, unscored{0};
     auto body = [&](int64_t i0, int64_t i1) {
-        int64_t nr = 0, nm = 0;
+        int64_t nr = 0, nm = 0, bad = 0;
         for (int64_t i = i0; i < i1; i++) {
             const float f = raw32[i];
-            if (f < kMinAccepted) { nr++; nm += std::signbit(f); out[i] = std::nan(""); }
+            if (f != f) { bad++; out[i] = std::nan(""); }           // an FP64-first pair the FP32 pass never scored: a bug
+            else if (f < kMinAccepted) { nr++; nm += std::signbit(f); out[i] = std::nan(""); }
             else out[i] = (double)(log10f(f) - log10_init_f);       // float subtraction, :142
             if (o32) o32[i] = std::fabs(f);     // the sign bit only marks pairs for the flush-exact FP64 tier
             if (o64) o64[i] = 0.0;
             if (ores) ores[i] = 0;
         }
-        need_rescue += nr; marked += nm;
+        need_rescue += nr; marked += nm; unscored += bad;
     };
     const int nt = (int)std::min<int64_t>(dc.pool->width(), std::max<int64_t>(1, p.n_pairs / 16384));
     dc.pool->parallel_for(nt, [&](int t) { body(p.n_pairs * t / nt, p.n_pairs * (t + 1) / nt); });
+    if (unscored.load()) { err = std::to_string(unscored.load()) + " pairs left unscored by the FP32 pass"; return PHMM_ERR_CUDA; }
     if (marked.load()) {
         // tier 3: pairs whose FP64 sum came out within reach of the denormal range are redone by the
         // flush-exact FP64 kernels now; they append to the same rescue list
@@ -1066,7 +1180,7 @@ int init_device(DeviceCtx& dc, int depth, std::string& err)
 void free_slot(Slot& s)
 {
     s.h_in.release(); s.h_jobs.release(); s.h_out.release(); s.h_rescue.release();
-    s.d_in.release(); s.d_jobs.release(); s.d_out.release(); s.d_rescue.release(); s.d_flags.release();
+    s.d_in.release(); s.d_jobs.release(); s.d_out.release(); s.d_rescue.release(); s.d_flags.release(); s.d_work.release();
     for (int i = 0; i < kAuxStreams; i++) {
         if (s.ev_join[i]) cudaEventDestroy(s.ev_join[i]);
         if (s.aux[i]) cudaStreamDestroy(s.aux[i]);
@@ -1121,7 +1235,14 @@ const char* phmm_strerror(int code)
     }
 }
 
-const char* phmm_last_error(const phmm_engine* e) { return e ? e->last_error.c_str() : ""; }
+const char* phmm_last_error(const phmm_engine* e)
+{
+    // a copy private to the calling thread: the engine's string may be rewritten by another thread's call
+    thread_local std::string copy;
+    if (!e) return "";
+    { std::lock_guard<std::mutex> lk(const_cast<phmm_engine*>(e)->mu); copy = e->last_error; }
+    return copy.c_str();
+}
 
 int phmm_tables(const float** ph2pr_f32, const float** mm_f32, const double** ph2pr_f64,
                 const double** mm_f64, int32_t* mm_entries)
@@ -1138,6 +1259,11 @@ int phmm_tables(const float** ph2pr_f32, const float** mm_f32, const double** ph
 int phmm_normalize_filter(double* lik, int32_t n_reads, int32_t n_haps, const int32_t* read_len, uint8_t* keep)
 {
     // intel_pairhmm.hpp:24-46; constants :19-23
+    if (!lik || !read_len || !keep || n_reads <= 0) return 0;
+    if (n_haps <= 0) {                       // no haplotypes: nothing to cap, no evidence against any read
+        for (int i = 0; i < n_reads; i++) keep[i] = 1;
+        return n_reads;
+    }
     int kept = 0;
     for (int i = 0; i < n_reads; i++) {
         double* row = lik + (size_t)i * n_haps;
@@ -1161,6 +1287,22 @@ int phmm_host_unregister(void* p)
 {
     if (!p) return PHMM_ERR_INVALID_ARG;
     return cudaHostUnregister(p) == cudaSuccess ? PHMM_OK : PHMM_ERR_CUDA;
+}
+
+int phmm_host_alloc(size_t bytes, void** out)
+{
+    if (!out || !bytes) return PHMM_ERR_INVALID_ARG;
+    *out = nullptr;
+    const cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    if (e == cudaSuccess) return PHMM_OK;
+    cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? PHMM_ERR_OOM : (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? PHMM_ERR_NO_DEVICE : PHMM_ERR_CUDA;
+}
+
+int phmm_host_free(void* p)
+{
+    if (!p) return PHMM_ERR_INVALID_ARG;
+    return cudaFreeHost(p) == cudaSuccess ? PHMM_OK : PHMM_ERR_CUDA;
 }
 
 int phmm_plan(const phmm_batch* b, int32_t sm_count, int32_t host_threads, phmm_plan_info* info,
@@ -1200,25 +1342,49 @@ int phmm_plan(const phmm_batch* b, int32_t sm_count, int32_t host_threads, phmm_
     return PHMM_OK;
 }
 
+// everything a device context owns on the device (also the failure path of phmm_create)
+static void teardown_device(DeviceCtx& dc)
+{
+    cudaSetDevice(dc.ordinal);
+    for (auto& s : dc.slots) { if (s.stream) cudaStreamSynchronize(s.stream); free_slot(s); }
+    dc.slots.clear();
+    cudaFree(dc.d_ph2pr_f); cudaFree(dc.d_mm_f); cudaFree(dc.d_ph2pr_d); cudaFree(dc.d_mm_d);
+    dc.d_ph2pr_f = dc.d_mm_f = nullptr; dc.d_ph2pr_d = dc.d_mm_d = nullptr;
+}
+
 int phmm_create(const phmm_options* opt, phmm_engine** out)
 {
     if (!out) return PHMM_ERR_INVALID_ARG;
     *out = nullptr;
+    DeviceGuard guard;
     std::unique_ptr<phmm_engine> e(new phmm_engine());
     if (opt) std::memcpy(&e->opt, opt, std::min<size_t>(sizeof(phmm_options), opt->struct_size > 0 ? (size_t)opt->struct_size : sizeof(phmm_options)));
     int n_dev = std::max(1, e->opt.n_devices);
     int depth = e->opt.pipeline_depth > 0 ? e->opt.pipeline_depth : 2;
     e->host_threads = std::max(1, e->opt.host_threads);
+    static const bool trace_init = getenv("PHMM_TRACE_INIT") != nullptr;
+    const auto ti0 = std::chrono::steady_clock::now();
+    auto since = [&](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
     int visible = 0;
     if (cudaGetDeviceCount(&visible) != cudaSuccess || visible == 0) return PHMM_ERR_NO_DEVICE;
+    if (trace_init) fprintf(stderr, "phmm init trace: cudaGetDeviceCount (driver init) %.1f ms\n", since(ti0));
     std::string err;
+    auto fail = [&](int rc) {                 // devices 0..d-1 are already initialised: give their memory back
+        for (auto& dc : e->devs) teardown_device(*dc);
+        return rc;
+    };
     for (int d = 0; d < n_dev; d++) {
         std::unique_ptr<DeviceCtx> dc(new DeviceCtx());
         dc->ordinal = (opt && opt->devices) ? opt->devices[d] : d;
-        if (dc->ordinal < 0 || dc->ordinal >= visible) return PHMM_ERR_NO_DEVICE;
+        if (dc->ordinal < 0 || dc->ordinal >= visible) return fail(PHMM_ERR_NO_DEVICE);
+        // (an ordinal may be listed more than once: every entry is an independent worker with its own streams,
+        //  tables and pools, which lets the sharding / gather path be exercised on a one-GPU box)
         dc->pool.reset(new HostPool(e->host_threads - 1));
+        dc->fp64_first_opt = e->opt.fp64_first;
+        const auto tid = std::chrono::steady_clock::now();
         int rc = init_device(*dc, depth, err);
-        if (rc) { fprintf(stderr, "phmm_create: %s\n", err.c_str()); return rc; }
+        if (trace_init) fprintf(stderr, "phmm init trace: device %d context + tables + %d slots %.1f ms\n", dc->ordinal, depth, since(tid));
+        if (rc) { fprintf(stderr, "phmm_create: %s\n", err.c_str()); teardown_device(*dc); return fail(rc); }
         e->devs.push_back(std::move(dc));
     }
     for (auto& dc : e->devs) { dc->worker.start(dc->ordinal); dc->packer.start(dc->ordinal); }
@@ -1229,19 +1395,41 @@ int phmm_create(const phmm_options* opt, phmm_engine** out)
 void phmm_destroy(phmm_engine* e)
 {
     if (!e) return;
+    DeviceGuard guard;
     for (auto& dc : e->devs) {
         dc->packer.finish();      // a pack task may still post its launch task to the worker: packer first
         dc->worker.finish();
-        cudaSetDevice(dc->ordinal);
-        for (auto& s : dc->slots) { if (s.stream) cudaStreamSynchronize(s.stream); free_slot(s); }
-        cudaFree(dc->d_ph2pr_f); cudaFree(dc->d_mm_f); cudaFree(dc->d_ph2pr_d); cudaFree(dc->d_mm_d);
+        teardown_device(*dc);
     }
     delete e;
+}
+
+// Drain the slots of a ticket whose results nobody will fetch (a failed submit, a wait without an output
+// buffer): every device that packed has a stage_launch task queued on its worker and copies in flight on the
+// slot's stream -- with PHMM_BATCH_PINNED_INPUTS straight out of the caller's memory.  The drain task lands
+// BEHIND that launch task on the same worker, synchronises the stream, and only then is the slot reusable.
+static void drain_parts(phmm_engine* e, const std::vector<std::pair<int, int>>& parts)
+{
+    if (parts.empty()) return;
+    Latch latch((int)parts.size());
+    for (const auto& pr : parts) {
+        DeviceCtx* dcp = e->devs[pr.first].get();
+        Slot* sp = &dcp->slots[pr.second];
+        dcp->post([sp, &latch] {
+            if (sp->stream) cudaStreamSynchronize(sp->stream);
+            for (int i = 0; i < kAuxStreams; i++) if (sp->aux[i]) cudaStreamSynchronize(sp->aux[i]);
+            latch.done();
+        });
+    }
+    latch.wait();
+    std::lock_guard<std::mutex> lk(e->mu);
+    for (const auto& pr : parts) e->devs[pr.first]->slots[pr.second].busy = false;
 }
 
 int phmm_submit(phmm_engine* e, const phmm_batch* b, phmm_ticket* t)
 {
     if (!e || !t) return PHMM_ERR_INVALID_ARG;
+    DeviceGuard guard;
     std::string err;
     int rc = validate_batch(b, err);
     if (rc) { e->set_error(err); return rc; }
@@ -1254,24 +1442,33 @@ int phmm_submit(phmm_engine* e, const phmm_batch* b, phmm_ticket* t)
     std::vector<std::string> errs(nd);
     std::vector<int> slot_of(nd, -1);
     int active = 0;
-    for (int d = 0; d < nd; d++) {
-        if (cut[d + 1] == cut[d]) continue;
-        DeviceCtx& dc = *e->devs[d];
-        const int si = dc.next_slot;
-        if (dc.slots[si].busy) { e->set_error("all pipeline slots in flight: call phmm_wait first"); return PHMM_ERR_INVALID_ARG; }
-        slot_of[d] = si;
-        active++;
+    {   // slot ring state (busy, next_slot) is shared with phmm_wait, which may run on another thread
+        std::lock_guard<std::mutex> lk(e->mu);
+        for (int d = 0; d < nd; d++) {
+            if (cut[d + 1] == cut[d]) continue;
+            DeviceCtx& dc = *e->devs[d];
+            if (dc.slots[dc.next_slot].busy) {
+                e->last_error = "all pipeline slots in flight: call phmm_wait first";
+                return PHMM_ERR_INVALID_ARG;
+            }
+        }
+        for (int d = 0; d < nd; d++) {
+            if (cut[d + 1] == cut[d]) continue;
+            DeviceCtx& dc = *e->devs[d];
+            slot_of[d] = dc.next_slot;
+            dc.slots[dc.next_slot].busy = true;
+            dc.next_slot = (dc.next_slot + 1) % (int)dc.slots.size();
+            active++;
+        }
     }
     Latch latch(active);
     for (int d = 0; d < nd; d++) {
         if (slot_of[d] < 0) continue;
         DeviceCtx& dc = *e->devs[d];
         Slot& s = dc.slots[slot_of[d]];
-        s.busy = true;
-        dc.next_slot = (dc.next_slot + 1) % (int)dc.slots.size();
         const int64_t out0 = batch_pairs(b, 0, cut[d]);
         const int g0 = cut[d], g1 = cut[d + 1];
-        const bool exact = e->opt.exact_fp32 != 0;
+        const bool exact = e->opt.exact_fp32 != 0, use_double = e->opt.use_double != 0;
         s.async_rc = PHMM_OK; s.async_err.clear();
         Slot* sp = &s;
         DeviceCtx* dcp = &dc;
@@ -1287,7 +1484,7 @@ int phmm_submit(phmm_engine* e, const phmm_batch* b, phmm_ticket* t)
             if (rc) { *rc_out = rc; *err_out = local_err; lp->done(); return; }
             dcp->post([=] {               // queued BEFORE the release: a phmm_wait that follows lands behind it
                 std::string e2;
-                const int rc2 = stage_launch(*dcp, *sp, exact, true, e2);
+                const int rc2 = stage_launch(*dcp, *sp, exact, use_double, true, e2);
                 if (rc2) { sp->async_rc = rc2; sp->async_err = e2; }
             });
             lp->done();
@@ -1297,8 +1494,10 @@ int phmm_submit(phmm_engine* e, const phmm_batch* b, phmm_ticket* t)
     latch.wait();     // caller's arrays are copied: they may be released now
     for (int d = 0; d < nd; d++)
         if (rcs[d]) {
+            // one device failed to pack: the others already have uploads and launches under way.  Wait them out
+            // before the slots are handed back and before the caller is told its arrays are its own again.
+            drain_parts(e, rec.parts);
             e->set_error(errs[d]);
-            for (auto& pr : rec.parts) e->devs[pr.first]->slots[pr.second].busy = false;
             return rcs[d];
         }
     std::lock_guard<std::mutex> lk(e->mu);
@@ -1310,6 +1509,7 @@ int phmm_submit(phmm_engine* e, const phmm_batch* b, phmm_ticket* t)
 int phmm_wait(phmm_engine* e, phmm_ticket t, phmm_result* r)
 {
     if (!e || !r) return PHMM_ERR_INVALID_ARG;
+    DeviceGuard guard;
     TicketRec rec;
     {
         std::lock_guard<std::mutex> lk(e->mu);
@@ -1319,7 +1519,7 @@ int phmm_wait(phmm_engine* e, phmm_ticket t, phmm_result* r)
         e->tickets.erase(it);
     }
     if (rec.n_pairs && !r->log10_lik) {
-        for (auto& pr : rec.parts) e->devs[pr.first]->slots[pr.second].busy = false;
+        drain_parts(e, rec.parts);            // the ticket is consumed: let its work finish, then free the slots
         e->set_error("result->log10_lik is NULL");
         return PHMM_ERR_INVALID_ARG;
     }
@@ -1329,27 +1529,29 @@ int phmm_wait(phmm_engine* e, phmm_ticket t, phmm_result* r)
     Latch latch(np);
     for (int k = 0; k < np; k++) {
         DeviceCtx& dc = *e->devs[rec.parts[k].first];
-        Slot& s = dc.slots[rec.parts[k].second];
         dc.post([&, k] {
             rcs[k] = finalize_part(e, *e->devs[rec.parts[k].first], e->devs[rec.parts[k].first]->slots[rec.parts[k].second], r, errs[k]);
             latch.done();
         });
-        (void)s;
     }
     latch.wait();
     phmm_stats st{};
     st.n_pairs = rec.n_pairs;
     int rc_all = PHMM_OK;
-    for (int k = 0; k < np; k++) {
-        Slot& s = e->devs[rec.parts[k].first]->slots[rec.parts[k].second];
-        const Part& p = s.part;
-        st.n_cells += p.n_cells; st.n_rescued += p.rescue_count;
-        st.h2d_bytes += (int64_t)p.h2d_bytes; st.d2h_bytes += (int64_t)p.d2h_bytes;
-        st.kernel_launches += p.launches;
-        st.kernel_ms = std::max(st.kernel_ms, p.kernel_ms);
-        st.n_devices_used++;
-        s.busy = false;
-        if (rcs[k] && !rc_all) { rc_all = rcs[k]; e->set_error(errs[k]); }
+    std::string first_err;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        for (int k = 0; k < np; k++) {
+            Slot& s = e->devs[rec.parts[k].first]->slots[rec.parts[k].second];
+            const Part& p = s.part;
+            st.n_cells += p.n_cells; st.n_rescued += p.rescue_count;
+            st.h2d_bytes += (int64_t)p.h2d_bytes; st.d2h_bytes += (int64_t)p.d2h_bytes;
+            st.kernel_launches += p.launches;
+            st.kernel_ms = std::max(st.kernel_ms, p.kernel_ms);
+            st.n_devices_used++;
+            s.busy = false;
+            if (rcs[k] && !rc_all) { rc_all = rcs[k]; e->last_error = errs[k]; }
+        }
     }
     st.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - rec.t0).count();
     r->stats = st;
@@ -1382,7 +1584,7 @@ int phmm_stage(phmm_engine* e, const phmm_batch* b, phmm_staged** out)
         auto go = [&]() -> int {
             int rc1 = init_slot(s, err);
             if (rc1) return rc1;
-            int rc2 = stage_and_launch(dc, s, b, 0, b->n_regions, 0, e->opt.exact_fp32 != 0, false, err);
+            int rc2 = stage_and_launch(dc, s, b, 0, b->n_regions, 0, e->opt.exact_fp32 != 0, e->opt.use_double != 0, false, err);
             if (rc2) return rc2;
             CUDA_TRY(cudaStreamSynchronize(s.stream));
             return PHMM_OK;
@@ -1415,7 +1617,7 @@ int phmm_run_staged_ex(phmm_engine* e, phmm_staged* st, int32_t iters, float* ms
             static const bool skip_rescue = getenv("PHMM_EXP_SKIP_RESCUE") != nullptr;   // timing experiments only
             // device time of `iters` back-to-back passes: sum of the per-pass [ev_k0, ev_k1] brackets
             for (int it = 0; it < iters; it++) {
-                int rc2 = launch_kernels(s, exact, 1, skip_rescue ? 1 : 2, err);
+                int rc2 = launch_kernels(s, exact, 1, skip_rescue ? 1 : 2, err, e->opt.use_double != 0);
                 if (rc2) return rc2;
                 CUDA_TRY(cudaEventSynchronize(s.ev_k1));
                 float one = 0.f;
@@ -1470,7 +1672,7 @@ int phmm_run_staged_pipelined(phmm_engine* e, phmm_staged* const* sts, int32_t n
             for (int i = 1; i < std::min(n, steps); i++) CUDA_TRY(cudaStreamWaitEvent(sts[i]->slot.stream, ev_begin, 0));
             for (int it = 0; it < steps; it++) {
                 Slot& s = sts[it % n]->slot;
-                int rc2 = launch_kernels(s, exact, 1, 2, err);
+                int rc2 = launch_kernels(s, exact, 1, 2, err, e->opt.use_double != 0);
                 if (rc2) return rc2;
                 nl += s.part.launches;
             }

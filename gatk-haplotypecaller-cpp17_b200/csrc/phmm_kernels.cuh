@@ -68,6 +68,25 @@ constexpr float kMinAccepted = 1e-28f;   // pairhmm/native/pairhmm_common.h:16
 // redone by the EXACT FP64 kernel, whose products are flushed by hand.  The FP64 kernel marks them by
 // setting the sign bit of their raw FP32 sum and the (job, chunk) flag to 2.
 constexpr double kFlushDanger = 1e-285;
+// FP64-FIRST order (tier 0), used when the previous batch redid most of its pairs in FP64: every pair is scored
+// in FP64 first, and the FP32 pass -- whose only purpose would be to find out that the pair underflows -- is
+// skipped wherever the FP64 sum PROVES that it would.  The FP32 kernel computes the same positive recurrence
+// with factors that differ from the FP64 ones by <= 1.3e-6 relative (separately generated tables,
+// native/Context.h:141-174) and rounds every operation to 2^-24 relative; along any path of R + H <= 8447
+// cells that compounds to < 2% (flush-to-zero only makes the FP32 value smaller).  So an FP64 sum below HALF of
+// the rescue threshold -- rescaled from 2^1020 to 2^120, i.e. 0.5e-28 * 2^900 -- guarantees raw FP32 < 1e-28f
+// (intel_pairhmm.hpp:137) with a margin of 2x against that 2%: the pair goes straight to the rescue list with
+// raw FP32 reported as 0.0f.  Every other pair is marked kNeedsF32 and gets the ordinary FP32 pass (and, if that
+// does underflow after all, the ordinary FP64 redo): identical decisions, identical log10 values.
+constexpr double kCertainUnderflow64 = 0.5e-28 * 8.452712498170644e+270;   // 0.5e-28 * 2^900
+constexpr uint32_t kNeedsF32 = 0x7fc00001u;                                // a NaN payload no computation produces
+// (job, chunk) flag byte: which later launches have work in this unit
+enum : unsigned { kFlagRedo64 = 1u, kFlagFlush64 = 2u, kFlagNeedsF32 = 4u };
+// OR into a flag byte (several warps / lanes may raise different bits of one byte: word-wide atomic)
+__device__ __forceinline__ void flag_or(uint8_t* flag, unsigned bits) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(flag);
+    atomicOr(reinterpret_cast<unsigned*>(a & ~(uintptr_t)3), bits << (8u * (unsigned)(a & 3)));
+}
 // Lane l+1 runs kSkew columns behind lane l.  With 2, the bottom row a lane shuffles down at the end
 // of a step is not consumed until a whole step later (shuffle latency off the X-chain critical path).
 // Measured on the final kernel: no gain (the other warps hide that latency) while the straddling
@@ -124,7 +143,20 @@ struct KernelArgs {
     int32_t    flag_hpj, flag_chunks;    // chunking of the FLAGS = the FP32 launch's haps_per_job and grid.y; an
                                          // FP64 launch may cut the haplotypes finer (its own haps_per_job)
     int32_t    tier;                     // FP64 launches: 2 = redo of FP32 underflows, 3 = flush-exact redo of the
-                                         // pairs whose FP64 sum came out within reach of the denormal range
+                                         // pairs whose FP64 sum came out within reach of the denormal range;
+                                         // 0 = FP64 FIRST (every pair; see kCertainUnderflow64)
+    // Work list (LIST instantiations).  A launch either walks the grid (blockIdx.x = job, blockIdx.y = haplotype
+    // chunk) or PULLS units from a compact list that build_work_list() made of the flag bytes an earlier launch
+    // of the same stream raised: a fixed, small grid of warps, each taking the next item with an atomic cursor
+    // until the list is exhausted.  An empty list costs a few microseconds instead of one CTA launch per
+    // (job, chunk) -- the FP64 redo of a batch without underflows used to cost 7% of the ragged window stream
+    // that way -- and a dense one is balanced dynamically.  Item = {unit, sub}: unit = job * flag_chunks + chunk
+    // in the flag chunking (flag_hpj haplotypes per chunk), sub = which haps_per_job-sized piece of that chunk.
+    const uint2* work_in;
+    const unsigned* work_in_count;
+    unsigned*  work_in_cursor;
+    int32_t    first64;                  // this chain started FP64 first: a raw FP32 sum of exactly 0 is a pair that
+                                         // is already on the rescue list (proven underflow), not one to redo
 };
 
 // ---- precision policies --------------------------------------------------------------------
@@ -269,7 +301,9 @@ enum : int { kModeGeneral = 0, kModeConst = 1, kModeConstShared = 2 };
 // reference's row 0 -- (0, 0, init_Y) -- instead of what the shuffle hands it from the group above:
 // zeroed factors annihilate the M and X it received, a select replaces the Y.  Lanes behind the last
 // group shadow group 0 with zero priors and never emit.
-template <class P, int K, int G, int MODE, bool EXACT, bool ALIGNED, bool PACKED = false>
+// LIST: the launch pulls its units from a work list (KernelArgs::work_in) instead of walking the grid; the FP32
+// LIST kernel is the selective pass of the FP64-first order (scores only the pairs marked kNeedsF32).
+template <class P, int K, int G, int MODE, bool EXACT, bool ALIGNED, bool PACKED = false, bool LIST = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, (P::kIsF32 && K <= 5 && MODE != kModeGeneral) ? PHMM_MIN_WARPS / kWarpsPerCta : 1)
 forward_kernel(const KernelArgs args)
 {
@@ -302,24 +336,42 @@ forward_kernel(const KernelArgs args)
     const int lane = threadIdx.x & 31;
     int grp = lane / G;                   // lane group and lane within it (PACKED: set once the job is known)
     int l   = lane % G;
-    const int job_idx = blockIdx.x * kWarpsPerCta + warp;
-    if (job_idx >= args.n_jobs) return;
+    const unsigned n_items = LIST ? *args.work_in_count : 0u;   // final: the list was built earlier in this stream
+#pragma unroll 1
+    for (;;) {                            // LIST: one unit per round; grid walk: a single round
+    int job_idx, h_first, h_cap;
+    if constexpr (LIST) {
+        unsigned i = 0;
+        if (lane == 0) i = atomicAdd(args.work_in_cursor, 1u);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= n_items) return;
+        const uint2 item = args.work_in[i];
+        const int chunk = (int)(item.x % (unsigned)args.flag_chunks);
+        job_idx = (int)(item.x / (unsigned)args.flag_chunks);
+        h_first = chunk * args.flag_hpj + (int)item.y * args.haps_per_job;
+        h_cap = min((chunk + 1) * args.flag_hpj, h_first + args.haps_per_job);
+        grp = lane / G; l = lane % G;
+        __syncwarp();                     // the previous unit's shared memory is free
+    } else {
+        job_idx = blockIdx.x * kWarpsPerCta + warp;
+        if (job_idx >= args.n_jobs) return;
+        h_first = blockIdx.y * args.haps_per_job;
+        h_cap = h_first + args.haps_per_job;
+    }
 
-    uint8_t* const my_flag = args.job_flags + ((size_t)(args.job_flag_base + job_idx) * args.flag_chunks +
-                                               (blockIdx.y * args.haps_per_job) / args.flag_hpj);
-    // nothing to redo here: one byte read, done.  (Several FP64 warps may share a flag byte, and one of them
-    // may already have raised it to 2 for tier 3, so tier 2 only tests for non-zero.)
-    if (!P::kIsF32 && (args.tier == 3 ? *my_flag != 2 : *my_flag == 0)) return;
-    // FP64: which pairs this launch redoes, told from their raw FP32 sum
+    uint8_t* const my_flag = args.job_flags + ((size_t)(args.job_flag_base + job_idx) * args.flag_chunks + h_first / args.flag_hpj);
+    // grid walk of an FP64 redo: nothing to redo here -> one byte read, done
+    if (!P::kIsF32 && !LIST && args.tier != 0 && !(*my_flag & (args.tier == 3 ? kFlagFlush64 : kFlagRedo64))) return;
+    // FP64: which pairs this launch redoes, told from their raw FP32 sum (tier 0, FP64 first: every pair)
     auto needs_redo = [&](const float raw) {
-        return args.tier == 3 ? (__float_as_uint(raw) >> 31) != 0u : raw < kMinAccepted;
+        return args.tier == 0 ? true : args.tier == 3 ? (__float_as_uint(raw) >> 31) != 0u
+                                                      : (raw < kMinAccepted && !(args.first64 && raw == 0.0f));
     };
     const WarpJob job = args.jobs[job_idx];
     const int hap_beg = args.region_hap_beg[job.region];
     const int nh      = args.region_hap_beg[job.region + 1] - hap_beg;
-    const int h_first = blockIdx.y * args.haps_per_job;
-    if (h_first >= nh) return;
-    const int h_last  = min(nh, h_first + args.haps_per_job);
+    if (h_first >= nh) { if constexpr (LIST) continue; else return; }
+    const int h_last  = min(nh, h_cap);
     const int rd_beg  = args.region_read_beg[job.region];
     const int64_t out_base = args.region_out_beg[job.region];
     int nl = G;                           // lanes per group
@@ -589,16 +641,22 @@ forward_kernel(const KernelArgs args)
                     const int64_t oi = out_base + (int64_t)(rd[hf] - rd_beg) * nh + h;
                     bool w = valid[hf] && group_live;
                     if (!P::kIsF32) w = w && needs_redo(args.raw32[oi]);
+                    if (P::kIsF32 && LIST) w = w && __float_as_uint(args.raw32[oi]) == kNeedsF32;    // selective pass
                     if (!w) continue;
                     const S res = P::sadd(P::get(sumM, hf), P::get(sumX, hf));
                     if (P::kIsF32) {
                         args.raw32[oi] = (float)res;
-                        if ((float)res < kMinAccepted) *my_flag = 1;
+                        if ((float)res < kMinAccepted) { if (LIST) flag_or(my_flag, kFlagRedo64); else *my_flag = (uint8_t)kFlagRedo64; }
+                    } else if (args.tier == 0 && !((double)res < kCertainUnderflow64)) {
+                        // FP64 first: the FP32 pass may NOT underflow here -- it has to be run to find out
+                        args.raw32[oi] = __uint_as_float(kNeedsF32);
+                        flag_or(my_flag, kFlagNeedsF32);
                     } else if (!EXACT && (double)res < kFlushDanger) {
-                        // tier 3 will redo this pair with flushed products
-                        args.raw32[oi] = __uint_as_float(__float_as_uint(args.raw32[oi]) | 0x80000000u);
-                        *my_flag = 2;
+                        // tier 3 will redo this pair with flushed products (FP64 first: its FP32 sum is a proven 0)
+                        args.raw32[oi] = __uint_as_float((args.tier == 0 ? 0u : __float_as_uint(args.raw32[oi])) | 0x80000000u);
+                        flag_or(my_flag, kFlagFlush64);
                     } else {
+                        if (args.tier == 0) args.raw32[oi] = 0.0f;     // proven < 1e-28f, never computed
                         const unsigned slot = atomicAdd(args.rescue_count, 1u);
                         args.rescue_out[slot].out_idx = oi;
                         args.rescue_out[slot].raw64 = (double)res;
@@ -656,6 +714,8 @@ forward_kernel(const KernelArgs args)
             }
         }
     }
+    if constexpr (!LIST) return;
+    }   // for (;;)
 }
 
 }  // namespace phmm

@@ -1,5 +1,6 @@
 // phmm_launch.h -- the compiled forward_kernel instantiations and how the planner names them.
 #pragma once
+#include <utility>
 #include "phmm_kernels.cuh"
 
 namespace phmm {
@@ -26,12 +27,14 @@ constexpr int kMaxReadLenCompiled = 32 * 8 - 1;   // 255
 constexpr int kLongMaxRead = 2048;           // == PHMM_MAX_READ_LEN (include/phmm.h)
 constexpr int kLongWarpsPerCta = 2;
 struct LongPair { int32_t read, hap; int64_t out_idx; };   // read / haplotype: indices into the part's offset arrays
-void launch_long_reads(const KernelArgs& args, const LongPair* pairs, int n_pairs, bool general, bool exact, cudaStream_t st);
+void launch_long_reads(const KernelArgs& args, const LongPair* pairs, int n_pairs, bool general, bool exact, bool use_double, cudaStream_t st);
 
 constexpr int kNumModes = 3;
-// tab[mode][aligned][shape]; aligned = every read length of the job is a multiple of K (constant-gap
-// modes only; the general mode has no aligned variant and its [1] row repeats [0])
-using KernelTab = KernelFn[kNumModes][2][kNumShapes];
+// tab[mode][aligned][shape][list]; aligned = every read length of the job is a multiple of K (constant-gap
+// modes only; the general mode has no aligned variant and its [1] row repeats [0]); list = the launch pulls its
+// units from a work list (phmm_kernels.cuh: LIST) -- compiled for the fast engines only (nullptr otherwise: the
+// exact engines walk the grid).
+using KernelTab = KernelFn[kNumModes][2][kNumShapes][2];
 
 // One translation unit per (precision, exact) keeps nvcc parallel; each fills its slice.
 void register_f32_fast(KernelTab& tab);
@@ -39,125 +42,35 @@ void register_f32_exact(KernelTab& tab);
 void register_f64_fast(KernelTab& tab);
 void register_f64_exact(KernelTab& tab);
 
-#define PHMM_REGISTER_ALL(POLICY, EXACT)                                                         \
-    do {                                                                                         \
-        for (int m_ = 0; m_ < kNumModes; m_++)                                                   \
-            for (int a_ = 0; a_ < 2; a_++)                                                       \
-                for (int s_ = kFirstPackedShape; s_ < kNumShapes; s_++) tab[m_][a_][s_] = nullptr; \
-        tab[1][1][18] = forward_kernel<POLICY, 8, 32, 1, EXACT, true, true>;                     \
-        tab[1][1][19] = forward_kernel<POLICY, 9, 32, 1, EXACT, true, true>;                     \
-        tab[1][1][20] = forward_kernel<POLICY, 10, 32, 1, EXACT, true, true>;                    \
-        tab[2][1][18] = forward_kernel<POLICY, 8, 32, 2, EXACT, true, true>;                     \
-        tab[2][1][19] = forward_kernel<POLICY, 9, 32, 2, EXACT, true, true>;                     \
-        tab[2][1][20] = forward_kernel<POLICY, 10, 32, 2, EXACT, true, true>;                    \
-        tab[0][0][0] = forward_kernel<POLICY, 1, 32, 0, EXACT, false>;                           \
-        tab[0][0][1] = forward_kernel<POLICY, 2, 32, 0, EXACT, false>;                           \
-        tab[0][0][2] = forward_kernel<POLICY, 3, 32, 0, EXACT, false>;                           \
-        tab[0][0][3] = forward_kernel<POLICY, 4, 32, 0, EXACT, false>;                           \
-        tab[0][0][4] = forward_kernel<POLICY, 5, 32, 0, EXACT, false>;                           \
-        tab[0][0][5] = forward_kernel<POLICY, 6, 32, 0, EXACT, false>;                           \
-        tab[0][0][6] = forward_kernel<POLICY, 7, 32, 0, EXACT, false>;                           \
-        tab[0][0][7] = forward_kernel<POLICY, 8, 32, 0, EXACT, false>;                           \
-        tab[0][0][8] = forward_kernel<POLICY, 1, 16, 0, EXACT, false>;                           \
-        tab[0][0][9] = forward_kernel<POLICY, 2, 16, 0, EXACT, false>;                           \
-        tab[0][0][10] = forward_kernel<POLICY, 3, 16, 0, EXACT, false>;                          \
-        tab[0][0][11] = forward_kernel<POLICY, 4, 16, 0, EXACT, false>;                          \
-        tab[0][0][12] = forward_kernel<POLICY, 5, 16, 0, EXACT, false>;                          \
-        tab[0][0][13] = forward_kernel<POLICY, 6, 16, 0, EXACT, false>;                          \
-        tab[0][0][14] = forward_kernel<POLICY, 7, 16, 0, EXACT, false>;                          \
-        tab[0][0][15] = forward_kernel<POLICY, 8, 16, 0, EXACT, false>;                          \
-        tab[0][0][16] = forward_kernel<POLICY, 9, 16, 0, EXACT, false>;                          \
-        tab[0][0][17] = forward_kernel<POLICY, 10, 16, 0, EXACT, false>;                         \
-        tab[0][1][0] = forward_kernel<POLICY, 1, 32, 0, EXACT, false>;                           \
-        tab[0][1][1] = forward_kernel<POLICY, 2, 32, 0, EXACT, false>;                           \
-        tab[0][1][2] = forward_kernel<POLICY, 3, 32, 0, EXACT, false>;                           \
-        tab[0][1][3] = forward_kernel<POLICY, 4, 32, 0, EXACT, false>;                           \
-        tab[0][1][4] = forward_kernel<POLICY, 5, 32, 0, EXACT, false>;                           \
-        tab[0][1][5] = forward_kernel<POLICY, 6, 32, 0, EXACT, false>;                           \
-        tab[0][1][6] = forward_kernel<POLICY, 7, 32, 0, EXACT, false>;                           \
-        tab[0][1][7] = forward_kernel<POLICY, 8, 32, 0, EXACT, false>;                           \
-        tab[0][1][8] = forward_kernel<POLICY, 1, 16, 0, EXACT, false>;                           \
-        tab[0][1][9] = forward_kernel<POLICY, 2, 16, 0, EXACT, false>;                           \
-        tab[0][1][10] = forward_kernel<POLICY, 3, 16, 0, EXACT, false>;                          \
-        tab[0][1][11] = forward_kernel<POLICY, 4, 16, 0, EXACT, false>;                          \
-        tab[0][1][12] = forward_kernel<POLICY, 5, 16, 0, EXACT, false>;                          \
-        tab[0][1][13] = forward_kernel<POLICY, 6, 16, 0, EXACT, false>;                          \
-        tab[0][1][14] = forward_kernel<POLICY, 7, 16, 0, EXACT, false>;                          \
-        tab[0][1][15] = forward_kernel<POLICY, 8, 16, 0, EXACT, false>;                          \
-        tab[0][1][16] = forward_kernel<POLICY, 9, 16, 0, EXACT, false>;                          \
-        tab[0][1][17] = forward_kernel<POLICY, 10, 16, 0, EXACT, false>;                         \
-        tab[1][0][0] = forward_kernel<POLICY, 1, 32, 1, EXACT, false>;                           \
-        tab[1][0][1] = forward_kernel<POLICY, 2, 32, 1, EXACT, false>;                           \
-        tab[1][0][2] = forward_kernel<POLICY, 3, 32, 1, EXACT, false>;                           \
-        tab[1][0][3] = forward_kernel<POLICY, 4, 32, 1, EXACT, false>;                           \
-        tab[1][0][4] = forward_kernel<POLICY, 5, 32, 1, EXACT, false>;                           \
-        tab[1][0][5] = forward_kernel<POLICY, 6, 32, 1, EXACT, false>;                           \
-        tab[1][0][6] = forward_kernel<POLICY, 7, 32, 1, EXACT, false>;                           \
-        tab[1][0][7] = forward_kernel<POLICY, 8, 32, 1, EXACT, false>;                           \
-        tab[1][0][8] = forward_kernel<POLICY, 1, 16, 1, EXACT, false>;                           \
-        tab[1][0][9] = forward_kernel<POLICY, 2, 16, 1, EXACT, false>;                           \
-        tab[1][0][10] = forward_kernel<POLICY, 3, 16, 1, EXACT, false>;                          \
-        tab[1][0][11] = forward_kernel<POLICY, 4, 16, 1, EXACT, false>;                          \
-        tab[1][0][12] = forward_kernel<POLICY, 5, 16, 1, EXACT, false>;                          \
-        tab[1][0][13] = forward_kernel<POLICY, 6, 16, 1, EXACT, false>;                          \
-        tab[1][0][14] = forward_kernel<POLICY, 7, 16, 1, EXACT, false>;                          \
-        tab[1][0][15] = forward_kernel<POLICY, 8, 16, 1, EXACT, false>;                          \
-        tab[1][0][16] = forward_kernel<POLICY, 9, 16, 1, EXACT, false>;                          \
-        tab[1][0][17] = forward_kernel<POLICY, 10, 16, 1, EXACT, false>;                         \
-        tab[1][1][0] = forward_kernel<POLICY, 1, 32, 1, EXACT, true>;                            \
-        tab[1][1][1] = forward_kernel<POLICY, 2, 32, 1, EXACT, true>;                            \
-        tab[1][1][2] = forward_kernel<POLICY, 3, 32, 1, EXACT, true>;                            \
-        tab[1][1][3] = forward_kernel<POLICY, 4, 32, 1, EXACT, true>;                            \
-        tab[1][1][4] = forward_kernel<POLICY, 5, 32, 1, EXACT, true>;                            \
-        tab[1][1][5] = forward_kernel<POLICY, 6, 32, 1, EXACT, true>;                            \
-        tab[1][1][6] = forward_kernel<POLICY, 7, 32, 1, EXACT, true>;                            \
-        tab[1][1][7] = forward_kernel<POLICY, 8, 32, 1, EXACT, true>;                            \
-        tab[1][1][8] = forward_kernel<POLICY, 1, 16, 1, EXACT, true>;                            \
-        tab[1][1][9] = forward_kernel<POLICY, 2, 16, 1, EXACT, true>;                            \
-        tab[1][1][10] = forward_kernel<POLICY, 3, 16, 1, EXACT, true>;                           \
-        tab[1][1][11] = forward_kernel<POLICY, 4, 16, 1, EXACT, true>;                           \
-        tab[1][1][12] = forward_kernel<POLICY, 5, 16, 1, EXACT, true>;                           \
-        tab[1][1][13] = forward_kernel<POLICY, 6, 16, 1, EXACT, true>;                           \
-        tab[1][1][14] = forward_kernel<POLICY, 7, 16, 1, EXACT, true>;                           \
-        tab[1][1][15] = forward_kernel<POLICY, 8, 16, 1, EXACT, true>;                           \
-        tab[1][1][16] = forward_kernel<POLICY, 9, 16, 1, EXACT, true>;                           \
-        tab[1][1][17] = forward_kernel<POLICY, 10, 16, 1, EXACT, true>;                          \
-        tab[2][0][0] = forward_kernel<POLICY, 1, 32, 2, EXACT, false>;                           \
-        tab[2][0][1] = forward_kernel<POLICY, 2, 32, 2, EXACT, false>;                           \
-        tab[2][0][2] = forward_kernel<POLICY, 3, 32, 2, EXACT, false>;                           \
-        tab[2][0][3] = forward_kernel<POLICY, 4, 32, 2, EXACT, false>;                           \
-        tab[2][0][4] = forward_kernel<POLICY, 5, 32, 2, EXACT, false>;                           \
-        tab[2][0][5] = forward_kernel<POLICY, 6, 32, 2, EXACT, false>;                           \
-        tab[2][0][6] = forward_kernel<POLICY, 7, 32, 2, EXACT, false>;                           \
-        tab[2][0][7] = forward_kernel<POLICY, 8, 32, 2, EXACT, false>;                           \
-        tab[2][0][8] = forward_kernel<POLICY, 1, 16, 2, EXACT, false>;                           \
-        tab[2][0][9] = forward_kernel<POLICY, 2, 16, 2, EXACT, false>;                           \
-        tab[2][0][10] = forward_kernel<POLICY, 3, 16, 2, EXACT, false>;                          \
-        tab[2][0][11] = forward_kernel<POLICY, 4, 16, 2, EXACT, false>;                          \
-        tab[2][0][12] = forward_kernel<POLICY, 5, 16, 2, EXACT, false>;                          \
-        tab[2][0][13] = forward_kernel<POLICY, 6, 16, 2, EXACT, false>;                          \
-        tab[2][0][14] = forward_kernel<POLICY, 7, 16, 2, EXACT, false>;                          \
-        tab[2][0][15] = forward_kernel<POLICY, 8, 16, 2, EXACT, false>;                          \
-        tab[2][0][16] = forward_kernel<POLICY, 9, 16, 2, EXACT, false>;                          \
-        tab[2][0][17] = forward_kernel<POLICY, 10, 16, 2, EXACT, false>;                         \
-        tab[2][1][0] = forward_kernel<POLICY, 1, 32, 2, EXACT, true>;                            \
-        tab[2][1][1] = forward_kernel<POLICY, 2, 32, 2, EXACT, true>;                            \
-        tab[2][1][2] = forward_kernel<POLICY, 3, 32, 2, EXACT, true>;                            \
-        tab[2][1][3] = forward_kernel<POLICY, 4, 32, 2, EXACT, true>;                            \
-        tab[2][1][4] = forward_kernel<POLICY, 5, 32, 2, EXACT, true>;                            \
-        tab[2][1][5] = forward_kernel<POLICY, 6, 32, 2, EXACT, true>;                            \
-        tab[2][1][6] = forward_kernel<POLICY, 7, 32, 2, EXACT, true>;                            \
-        tab[2][1][7] = forward_kernel<POLICY, 8, 32, 2, EXACT, true>;                            \
-        tab[2][1][8] = forward_kernel<POLICY, 1, 16, 2, EXACT, true>;                            \
-        tab[2][1][9] = forward_kernel<POLICY, 2, 16, 2, EXACT, true>;                            \
-        tab[2][1][10] = forward_kernel<POLICY, 3, 16, 2, EXACT, true>;                           \
-        tab[2][1][11] = forward_kernel<POLICY, 4, 16, 2, EXACT, true>;                           \
-        tab[2][1][12] = forward_kernel<POLICY, 5, 16, 2, EXACT, true>;                           \
-        tab[2][1][13] = forward_kernel<POLICY, 6, 16, 2, EXACT, true>;                           \
-        tab[2][1][14] = forward_kernel<POLICY, 7, 16, 2, EXACT, true>;                           \
-        tab[2][1][15] = forward_kernel<POLICY, 8, 16, 2, EXACT, true>;                           \
-        tab[2][1][16] = forward_kernel<POLICY, 9, 16, 2, EXACT, true>;                           \
-        tab[2][1][17] = forward_kernel<POLICY, 10, 16, 2, EXACT, true>;                          \
-    } while (0)
+template <class P, bool EXACT, bool LIST, int S>
+inline void register_shape(KernelTab& tab)
+{
+    constexpr int G = kShapes[S].G, K = kShapes[S].K;
+    constexpr int L = LIST ? 1 : 0;
+    if constexpr (S >= kFirstPackedShape) {          // PACKED: lane-aligned kernels of the constant-gap modes only
+        tab[0][0][S][L] = nullptr; tab[0][1][S][L] = nullptr; tab[1][0][S][L] = nullptr; tab[2][0][S][L] = nullptr;
+        tab[1][1][S][L] = forward_kernel<P, K, G, 1, EXACT, true, true, LIST>;
+        tab[2][1][S][L] = forward_kernel<P, K, G, 2, EXACT, true, true, LIST>;
+    } else {
+        tab[0][0][S][L] = tab[0][1][S][L] = forward_kernel<P, K, G, 0, EXACT, false, false, LIST>;
+        tab[1][0][S][L] = forward_kernel<P, K, G, 1, EXACT, false, false, LIST>;
+        tab[1][1][S][L] = forward_kernel<P, K, G, 1, EXACT, true, false, LIST>;
+        tab[2][0][S][L] = forward_kernel<P, K, G, 2, EXACT, false, false, LIST>;
+        tab[2][1][S][L] = forward_kernel<P, K, G, 2, EXACT, true, false, LIST>;
+    }
+}
+template <class P, bool EXACT, bool LIST, int... S>
+inline void register_shapes(KernelTab& tab, std::integer_sequence<int, S...>) { (register_shape<P, EXACT, LIST, S>(tab), ...); }
+
+// every Shape x MODE x aligned of one (precision, exact); WITH_LIST adds the work-list variants
+template <class P, bool EXACT, bool WITH_LIST>
+inline void register_all(KernelTab& tab)
+{
+    for (int m = 0; m < kNumModes; m++)
+        for (int a = 0; a < 2; a++)
+            for (int s = 0; s < kNumShapes; s++) tab[m][a][s][0] = tab[m][a][s][1] = nullptr;
+    register_shapes<P, EXACT, false>(tab, std::make_integer_sequence<int, kNumShapes>{});
+    if constexpr (WITH_LIST) register_shapes<P, EXACT, true>(tab, std::make_integer_sequence<int, kNumShapes>{});
+}
 
 }  // namespace phmm

@@ -136,7 +136,7 @@ __device__ __noinline__ S long_forward(const KernelArgs& args, const int ro, con
 
 template <bool EXACT>
 __global__ void __launch_bounds__(kLongWarpsPerCta * 32)
-long_read_kernel(const KernelArgs args, const LongPair* __restrict__ pairs, const int n_pairs, const int general)
+long_read_kernel(const KernelArgs args, const LongPair* __restrict__ pairs, const int n_pairs, const int general, const int use_double)
 {
     const int lane = threadIdx.x & 31;
     const int idx = blockIdx.x * kLongWarpsPerCta + (threadIdx.x >> 5);
@@ -144,7 +144,8 @@ long_read_kernel(const KernelArgs args, const LongPair* __restrict__ pairs, cons
     const LongPair p = pairs[idx];
     const int ro = args.read_off[p.read], R = args.read_off[p.read + 1] - ro;
     const int ho = args.hap_off[p.hap], H = args.hap_off[p.hap + 1] - ho;
-    const float f = long_forward<float, EXACT, false>(args, ro, R, ho, H, general != 0, lane);
+    // use_double: intel_pairhmm.hpp:135 `g_use_double ? 0.0f : compute_float(&tc)`
+    const float f = use_double ? 0.0f : long_forward<float, EXACT, false>(args, ro, R, ho, H, general != 0, lane);
     if (lane == 0) args.raw32[p.out_idx] = f;
     if (f < kMinAccepted) {                      // intel_pairhmm.hpp:137
         double d = long_forward<double, EXACT, EXACT>(args, ro, R, ho, H, general != 0, lane);
@@ -159,12 +160,12 @@ long_read_kernel(const KernelArgs args, const LongPair* __restrict__ pairs, cons
 
 }  // namespace
 
-void launch_long_reads(const KernelArgs& args, const LongPair* pairs, int n_pairs, bool general, bool exact, cudaStream_t st)
+void launch_long_reads(const KernelArgs& args, const LongPair* pairs, int n_pairs, bool general, bool exact, bool use_double, cudaStream_t st)
 {
     if (n_pairs <= 0) return;
     const int grid = (n_pairs + kLongWarpsPerCta - 1) / kLongWarpsPerCta;
-    if (exact) long_read_kernel<true><<<grid, kLongWarpsPerCta * 32, 0, st>>>(args, pairs, n_pairs, general ? 1 : 0);
-    else long_read_kernel<false><<<grid, kLongWarpsPerCta * 32, 0, st>>>(args, pairs, n_pairs, general ? 1 : 0);
+    if (exact) long_read_kernel<true><<<grid, kLongWarpsPerCta * 32, 0, st>>>(args, pairs, n_pairs, general ? 1 : 0, use_double ? 1 : 0);
+    else long_read_kernel<false><<<grid, kLongWarpsPerCta * 32, 0, st>>>(args, pairs, n_pairs, general ? 1 : 0, use_double ? 1 : 0);
 }
 
 }  // namespace phmm

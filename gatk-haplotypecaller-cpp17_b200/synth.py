@@ -165,6 +165,26 @@ def s5_stream(n_windows, seed=SEEDS["S5"], coverage=30, read_len=150, window=245
         yield B.from_regions(regions)
 
 
+def _s5_chunk(args):
+    n, seed = args
+    return next(s5_stream(n, seed=seed, windows_per_batch=n))
+
+
+def s5_batch(n_windows, seed=SEEDS["S5"], procs=None, chunk=256):
+    """One S5 batch of `n_windows` windows, generated in `chunk`-window pieces (piece k from seed + k, so the
+    result does not depend on the process count) on a process pool: the per-read python loop of s5_stream
+    makes ~350 windows/s on one core, far too slow for 8-GPU sized batches."""
+    import os
+    B = _batch_cls()
+    jobs = [(min(chunk, n_windows - o), seed + 7919 * k) for k, o in enumerate(range(0, n_windows, chunk))]
+    procs = procs or min(len(jobs), os.cpu_count() or 1)
+    if procs <= 1 or len(jobs) == 1:
+        return B.concat([_s5_chunk(j) for j in jobs])
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(procs) as pool:
+        return B.concat(pool.map(_s5_chunk, jobs))
+
+
 def random_small(seed, n_regions=3, max_reads=9, max_haps=5, max_read_len=70, max_hap_len=120,
                  general_gaps=True, n_frac=0.03, lower_frac=0.0):
     """Ragged little regions with N bases and arbitrary qualities: parity-test fodder."""

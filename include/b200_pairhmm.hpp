@@ -23,7 +23,10 @@
 // library's message (never falls back to a CPU implementation).
 #pragma once
 
+#include <algorithm>
 #include <cstdint>
+#include <cstdlib>
+#include <cstring>
 #include <deque>
 #include <memory>
 #include <mutex>
@@ -36,27 +39,130 @@
 namespace hc
 {
 
+// Process-wide engine (streams, memory pool, tables: created once, because the reference constructs its engine
+// object per region, haplotypecaller.hpp:90, and a CUDA context must not be).
+//
+// Configuration, in order of precedence: B200Engine::configure() before the first use; else the environment:
+//   PHMM_DEVICES=0,1,..    CUDA ordinals to shard regions over (default: device 0)
+//   PHMM_EXACT=1           unfused FP32 arithmetic in the reference's operation order: raw FP32 sums bit-identical
+//                          to compute_full_prob_avxs.  THIS is the mode that carries the bit-identical-VCF
+//                          guarantee; the default (FMA-contracted) mode agrees to <= 1e-4 log10 and can in
+//                          principle flip a `raw < 1e-28f` rescue decision or a GQ rounding.
+//   PHMM_USE_DOUBLE=1      the reference's g_use_double switch (intel_pairhmm.hpp:58,71,135)
+//   PHMM_HOST_THREADS=n    host threads per device for planning / packing / finalizing (default 4)
 class B200Engine
 {
 public:
-    // process-wide engine; `devices` empty = CUDA device 0
+    struct Config
+    {
+        std::vector<int32_t> devices;      // empty = CUDA device 0
+        bool exact = false;
+        bool use_double = false;
+        int pipeline_depth = 4;            // B200RegionBatcher keeps up to 3 batches in flight
+        int host_threads = 4;
+
+        bool operator==(const Config& o) const
+        { return devices == o.devices && exact == o.exact && use_double == o.use_double &&
+                 pipeline_depth == o.pipeline_depth && host_threads == o.host_threads; }
+
+        static Config from_env()
+        {
+            Config c;
+            if (const char* d = std::getenv("PHMM_DEVICES"))
+                for (const char* q = d; *q;) {
+                    char* end = nullptr;
+                    const long v = std::strtol(q, &end, 10);
+                    if (end == q) break;
+                    c.devices.push_back((int32_t)v);
+                    q = (*end == ',') ? end + 1 : end;
+                }
+            auto on = [](const char* name) { const char* v = std::getenv(name); return v && *v && *v != '0'; };
+            c.exact = on("PHMM_EXACT");
+            c.use_double = on("PHMM_USE_DOUBLE");
+            if (const char* t = std::getenv("PHMM_HOST_THREADS")) c.host_threads = std::max(1, std::atoi(t));
+            return c;
+        }
+    };
+
+    // Must come before the first get(); a second, different configuration is an error, not a silent no-op.
+    static void configure(const Config& c)
+    {
+        State& st = state();
+        std::lock_guard<std::mutex> lk(st.mu);
+        if (st.eng && !(st.cfg == c)) throw std::runtime_error("B200Engine::configure: the engine already exists with a different configuration");
+        st.cfg = c; st.configured = true;
+    }
+
+    // The engine; `devices` non-empty must name the devices it was (or is now) created with.
     static phmm_engine* get(const std::vector<int32_t>& devices = {})
     {
-        static std::mutex mu;
-        static phmm_engine* eng = nullptr;
-        std::lock_guard<std::mutex> lk(mu);
-        if (!eng) {
+        State& st = state();
+        std::lock_guard<std::mutex> lk(st.mu);
+        if (!st.eng) {
+            if (!st.configured) { st.cfg = Config::from_env(); st.configured = true; }
+            if (!devices.empty()) st.cfg.devices = devices;
             phmm_options opt{};
             opt.struct_size = (int32_t)sizeof(opt);
-            opt.n_devices = devices.empty() ? 1 : (int32_t)devices.size();
-            opt.devices = devices.empty() ? nullptr : devices.data();
-            opt.pipeline_depth = 4;            // B200RegionBatcher keeps up to 3 batches in flight
-            opt.host_threads = 4;              // planning, packing and the log10 pass of a batch
-            int rc = phmm_create(&opt, &eng);
-            if (rc != PHMM_OK) throw std::runtime_error(std::string("phmm_create: ") + phmm_strerror(rc));
+            opt.n_devices = st.cfg.devices.empty() ? 1 : (int32_t)st.cfg.devices.size();
+            opt.devices = st.cfg.devices.empty() ? nullptr : st.cfg.devices.data();
+            opt.pipeline_depth = st.cfg.pipeline_depth;
+            opt.host_threads = st.cfg.host_threads;
+            opt.exact_fp32 = st.cfg.exact ? 1 : 0;
+            opt.use_double = st.cfg.use_double ? 1 : 0;
+            int rc = phmm_create(&opt, &st.eng);
+            if (rc != PHMM_OK) { st.eng = nullptr; throw std::runtime_error(std::string("phmm_create: ") + phmm_strerror(rc)); }
+            // registered after the CUDA runtime's own exit handler (first touched inside phmm_create), so it
+            // runs before it: streams, pinned memory and worker threads go away while the context is alive
+            std::atexit([] { B200Engine::shutdown(); });
+        } else if (!devices.empty() && devices != effective_devices(st.cfg)) {
+            throw std::runtime_error("B200Engine::get: the engine already runs on a different device list");
         }
-        return eng;
+        return st.eng;
     }
+
+    static const Config& config() { return state().cfg; }
+
+    // Destroys the engine (all batchers must be drained and gone).  The next get() creates a new one.
+    static void shutdown()
+    {
+        State& st = state();
+        std::lock_guard<std::mutex> lk(st.mu);
+        if (st.eng) { phmm_destroy(st.eng); st.eng = nullptr; }
+    }
+
+private:
+    struct State { std::mutex mu; phmm_engine* eng = nullptr; Config cfg; bool configured = false; };
+    static State& state() { static State* s = new State(); return *s; }     // never destructed: no static-order races at exit
+    static std::vector<int32_t> effective_devices(const Config& c) { return c.devices.empty() ? std::vector<int32_t>{0} : c.devices; }
+};
+
+// Page-locked byte slab from the library (phmm_host_alloc): SoA arrays are gathered straight into it and
+// uploaded from it (PHMM_BATCH_PINNED_INPUTS) -- written once by the caller, read once by the DMA engine.
+class B200PinnedBytes
+{
+public:
+    B200PinnedBytes() = default;
+    B200PinnedBytes(const B200PinnedBytes&) = delete;
+    B200PinnedBytes& operator=(const B200PinnedBytes&) = delete;
+    ~B200PinnedBytes() { if (p_) phmm_host_free(p_); }
+    void reserve(std::size_t n)
+    {
+        if (n <= cap_) return;
+        std::size_t want = std::max<std::size_t>(n + n / 2, (std::size_t)1 << 20);
+        void* q = nullptr;
+        int rc = phmm_host_alloc(want, &q);
+        if (rc != PHMM_OK) throw std::runtime_error(std::string("phmm_host_alloc: ") + phmm_strerror(rc));
+        if (size_) std::memcpy(q, p_, size_);
+        if (p_) phmm_host_free(p_);
+        p_ = (uint8_t*)q; cap_ = want;
+    }
+    void append(const void* src, std::size_t n) { reserve(size_ + n); std::memcpy(p_ + size_, src, n); size_ += n; }
+    void clear() { size_ = 0; }
+    std::size_t size() const { return size_; }
+    const uint8_t* data() const { return p_; }
+private:
+    uint8_t* p_ = nullptr;
+    std::size_t cap_ = 0, size_ = 0;
 };
 
 struct B200PairHMM
@@ -169,20 +275,25 @@ public:
     template <class HaplotypeT, class ReadT>
     int add_region(const std::vector<HaplotypeT>& haps, const std::vector<ReadT>& reads)
     {
-        if (!cur_) cur_ = std::make_unique<Pending>();
+        if (!cur_) {
+            cur_ = std::make_unique<Pending>();
+            if (!free_slabs_.empty()) { cur_->slab = std::move(free_slabs_.back()); free_slabs_.pop_back(); }
+            else cur_->slab = std::make_unique<Slabs>();
+        }
         Pending& b = *cur_;
+        Slabs& sl = *b.slab;
         if (b.region_read_beg.empty()) { b.region_read_beg.push_back(0); b.region_hap_beg.push_back(0); b.read_off.push_back(0); b.hap_off.push_back(0); b.out_beg.push_back(0); }
         int64_t read_bytes = 0, hap_bytes = 0;
         for (const auto& r : reads) {
             if (r.SEQ.size() != r.QUAL.size()) throw std::runtime_error("B200RegionBatcher: SEQ and QUAL lengths differ");
-            b.read_bases.insert(b.read_bases.end(), r.SEQ.begin(), r.SEQ.end());
-            b.read_q.insert(b.read_q.end(), r.QUAL.begin(), r.QUAL.end());
-            b.read_off.push_back((int32_t)b.read_bases.size());
+            sl.read_bases.append(r.SEQ.data(), r.SEQ.size());       // gathered straight into page-locked memory
+            sl.read_q.append(r.QUAL.data(), r.QUAL.size());
+            b.read_off.push_back((int32_t)sl.read_bases.size());
             read_bytes += (int64_t)r.SEQ.size();
         }
         for (const auto& h : haps) {
-            b.hap_bases.insert(b.hap_bases.end(), h.bases.begin(), h.bases.end());
-            b.hap_off.push_back((int32_t)b.hap_bases.size());
+            sl.hap_bases.append(h.bases.data(), h.bases.size());
+            b.hap_off.push_back((int32_t)sl.hap_bases.size());
             hap_bytes += (int64_t)h.bases.size();
         }
         b.region_read_beg.push_back((int32_t)(b.read_off.size() - 1));
@@ -208,19 +319,17 @@ public:
         pb.region_read_beg = b.region_read_beg.data();
         pb.region_hap_beg = b.region_hap_beg.data();
         pb.read_off = b.read_off.data();
-        pb.read_bases = b.read_bases.data();
-        pb.read_q = b.read_q.data();
+        pb.read_bases = b.slab->read_bases.data();
+        pb.read_q = b.slab->read_q.data();
+        pb.flags = PHMM_BATCH_PINNED_INPUTS;                            // uploaded in place; the slab lives until the wait
         pb.read_i = pb.read_d = pb.read_c = nullptr;                   // constant strings of sam/sam.hpp:30-32
         pb.gap_open_i = (uint8_t)B200PairHMM::GAP_OPEN; pb.gap_open_d = (uint8_t)B200PairHMM::GAP_OPEN;
         pb.gap_cont_c = (uint8_t)B200PairHMM::GAP_CONT;
         pb.hap_off = b.hap_off.data();
-        pb.hap_bases = b.hap_bases.data();
+        pb.hap_bases = b.slab->hap_bases.data();
         b.lik.resize((size_t)b.out_beg.back());
         int rc = phmm_submit(eng_, &pb, &b.ticket);
         if (rc != PHMM_OK) throw std::runtime_error(std::string("phmm_submit: ") + phmm_strerror(rc) + ": " + phmm_last_error(eng_));
-        // inputs were copied to pinned staging; keep only what take() needs
-        b.read_bases.clear(); b.read_bases.shrink_to_fit(); b.read_q.clear(); b.read_q.shrink_to_fit();
-        b.hap_bases.clear(); b.hap_bases.shrink_to_fit();
         b.submitted = true;
         ++in_flight_; ++batches_submitted;
         batches_.push_back(std::move(cur_));
@@ -265,10 +374,14 @@ public:
     phmm_stats total_stats{};          // summed over finished batches (kernel_ms: sum, not max)
 
 private:
+    struct Slabs {
+        B200PinnedBytes read_bases, read_q, hap_bases;
+        void clear() { read_bases.clear(); read_q.clear(); hap_bases.clear(); }
+    };
     struct Pending {
         std::vector<int32_t> region_read_beg, region_hap_beg, read_off, hap_off;
         std::vector<int64_t> out_beg;
-        std::vector<uint8_t> read_bases, read_q, hap_bases;
+        std::unique_ptr<Slabs> slab;          // page-locked byte arrays; back to the free list once the batch is done
         std::vector<double> lik;
         int64_t cells = 0;
         phmm_ticket ticket = 0;
@@ -286,6 +399,7 @@ private:
             int rc = phmm_wait(eng_, b.ticket, &res);
             if (rc != PHMM_OK) throw std::runtime_error(std::string("phmm_wait: ") + phmm_strerror(rc) + ": " + phmm_last_error(eng_));
             b.done = true; --in_flight_;
+            b.slab->clear(); free_slabs_.push_back(std::move(b.slab));
             total_stats.n_pairs += res.stats.n_pairs; total_stats.n_cells += res.stats.n_cells;
             total_stats.n_rescued += res.stats.n_rescued; total_stats.h2d_bytes += res.stats.h2d_bytes;
             total_stats.d2h_bytes += res.stats.d2h_bytes; total_stats.kernel_launches += res.stats.kernel_launches;
@@ -300,6 +414,7 @@ private:
     int max_in_flight_;
     phmm_engine* eng_;
     std::unique_ptr<Pending> cur_;
+    std::vector<std::unique_ptr<Slabs>> free_slabs_;
     std::deque<std::unique_ptr<Pending>> batches_;
     std::vector<Where> where_;
     int next_batch_id_ = 0, first_batch_id_ = 0;

@@ -72,8 +72,16 @@ typedef struct phmm_options {
     const int32_t* devices;     /* CUDA ordinals; NULL = 0..n_devices-1                        */
     int32_t pipeline_depth;     /* in-flight batches per device (streams + buffers); 0 = 2     */
     int32_t exact_fp32;         /* 1: unfused mul/add, raw FP32 bit-identical to the reference */
-    int32_t host_threads;       /* threads for the log10 finalize step; 0 = 1                  */
-    int32_t reserved[3];
+    int32_t host_threads;       /* threads for planning, packing and finalizing a batch; 0 = 1 */
+    int32_t use_double;         /* 1: the reference's g_use_double switch (intel_pairhmm.hpp:58,71,135): the FP32
+                                   pass is skipped (its raw result is 0.0f) and EVERY pair is scored in FP64  */
+    int32_t fp64_first;         /* order of the precision passes.  0 (auto): FP32 first; FP64 FIRST for a batch
+                                   when the device's previous batch redid > 75% of its pairs in FP64 -- every
+                                   pair is then scored in FP64 and the FP32 pass only runs where the FP64 sum
+                                   does not prove the underflow (identical log10 values and rescue decisions;
+                                   the optional raw32 output of a proven underflow is 0.0f).  1: never.  2: always.
+                                   Ignored (never) with exact_fp32, whose raw FP32 sums are part of the contract. */
+    int32_t reserved[1];
 } phmm_options;
 
 /*
@@ -112,6 +120,13 @@ typedef struct phmm_batch {
 #define PHMM_BATCH_PINNED_INPUTS 1
 int  phmm_host_register(void* p, size_t bytes);      /* cudaHostRegister / cudaHostUnregister for callers   */
 int  phmm_host_unregister(void* p);                  /* without a CUDA toolchain of their own               */
+/* Page-locked host memory handed out by the library (cudaHostAlloc, portable across devices): a caller that
+ * GATHERS its reads into the SoA arrays anyway (the reference's reads are one std::string each,
+ * sam/sam.hpp:14-28) gathers straight into such a slab and submits with PHMM_BATCH_PINNED_INPUTS -- the bytes
+ * are then written once by the caller and read once by the DMA engine, with no staging copy in between.
+ * hc::B200RegionBatcher (include/b200_pairhmm.hpp) does exactly that. */
+int  phmm_host_alloc(size_t bytes, void** out);
+int  phmm_host_free(void* p);
 
 typedef struct phmm_stats {
     int64_t n_pairs, n_cells, n_rescued;
@@ -130,6 +145,14 @@ typedef struct phmm_result {
     phmm_stats stats;       /* out */
 } phmm_result;
 
+/*
+ * Threading contract.  phmm_create / phmm_destroy: one thread, nothing else in flight.  phmm_submit (and
+ * phmm_compute, phmm_stage, phmm_run_staged*) : ONE submitting thread at a time per engine.  phmm_wait may run
+ * on a different thread than phmm_submit (producer / consumer): the slot ring, the ticket table and the error
+ * string are guarded by the engine's mutex; tickets may be waited in any order, each once.
+ * phmm_last_error returns a copy private to the calling thread, valid until that thread's next call of it.
+ * Every entry point leaves the calling thread's current CUDA device unchanged.
+ */
 int  phmm_create(const phmm_options* opt, phmm_engine** out);
 void phmm_destroy(phmm_engine* e);
 int  phmm_compute(phmm_engine* e, const phmm_batch* b, phmm_result* r);

@@ -274,6 +274,102 @@ def test_submit_wait_pipeline_and_staged_path(pkg, engine, oracle):
     assert np.array_equal(res.log10.view(np.uint64), sync[2].view(np.uint64))
 
 
+def test_run_staged_pipelined_gives_the_same_bits_as_compute(pkg, engine):
+    """The path bench.py times (`value`): steps issued back to back, step i on staged batch i % n, every batch
+    on its own stream so FP32 and FP64 launches of neighbouring steps overlap.  Every batch -- with and
+    without FP64 redos, single- and multi-shape -- must come back with the bits phmm_compute gives."""
+    batches = [pkg.synth.s3(3, seed=11), pkg.synth.s4(2, n_reads=24, n_haps=4, seed=12), pkg.synth.s5_batch(48, seed=13),
+               pkg.synth.s2(6, seed=14), pkg.synth.random_small(15, n_regions=9, max_reads=30, max_haps=6)]
+    want = [engine.compute(b) for b in batches]
+    staged = [engine.stage(b) for b in batches]
+    try:
+        for steps in (len(batches), 3 * len(batches) + 2):           # the second round re-runs batches on their own streams
+            ms, launches = engine.run_staged_pipelined(staged, steps)
+            assert ms > 0 and launches >= 2 * steps
+            for b, st, w in zip(batches, staged, want):
+                got = engine.fetch_staged(st, b.n_pairs)
+                assert np.array_equal(got.log10.view(np.uint64), w.log10.view(np.uint64))
+                assert np.array_equal(got.rescued, w.rescued)
+                assert got.stats["n_rescued"] == w.stats["n_rescued"]
+    finally:
+        for st in staged:
+            engine.free_staged(st)
+
+
+@pytest.mark.parametrize("name,make", [
+    ("S4 long, all rescued", lambda s: s.s4(3, n_reads=24, n_haps=5)),
+    ("S3: hardly any pair rescued", lambda s: s.s3(1)),
+    ("mixed: good and hopeless reads, ragged", lambda s: s.random_small(91, n_regions=12, max_reads=30, max_haps=9, max_read_len=200,
+                                                                         max_hap_len=300, general_gaps=False)),
+    ("mixed, per-base gap penalties", lambda s: s.random_small(92, n_regions=8, max_reads=20, max_haps=6, max_read_len=200, max_hap_len=300)),
+    ("every length", lambda s: s.random_small(93, n_regions=30, max_reads=12, max_haps=4, max_read_len=255, max_hap_len=97, general_gaps=False)),
+])
+def test_fp64_first_order_gives_identical_results(pkg, engine, oracle, name, make):
+    """phmm_options.fp64_first = 2: every pair is scored in FP64 first and the FP32 pass only runs where the FP64 sum
+    does not prove the underflow (phmm_kernels.cuh: kCertainUnderflow64).  log10 values and rescue decisions must be
+    BIT-IDENTICAL to the FP32-first order, and within tolerance of the oracle."""
+    b = make(pkg.synth)
+    want = engine.compute(b)
+    with pkg.PairHMMEngine(devices=[0], fp64_first=2) as eng:
+        for _ in range(2):                                   # twice: the second batch also sees last_rescue_frac
+            got = eng.compute(b)
+            assert np.array_equal(got.rescued, want.rescued), name
+            assert np.array_equal(got.log10.view(np.uint64), want.log10.view(np.uint64)), name
+            assert got.stats["n_rescued"] == want.stats["n_rescued"]
+            keep = ~want.rescued.astype(bool)                # raw FP32 of a scored pair is the same number
+            assert np.array_equal(got.raw32[keep].view(np.uint32), want.raw32[keep].view(np.uint32)), name
+            assert np.array_equal(got.raw64.view(np.uint64), want.raw64.view(np.uint64)), name
+    check(want, oracle.batch(b, threads=16), what=name)
+
+
+def test_fp64_first_kicks_in_after_a_dense_batch(pkg, oracle):
+    """Auto mode: the order follows the device's previous batch (> 75% redone -> FP64 first), and falls back."""
+    dense, sparse = pkg.synth.s4(2, n_reads=24, n_haps=4), pkg.synth.s3(1)
+    with pkg.PairHMMEngine(devices=[0]) as eng:
+        seq = [dense, dense, sparse, sparse, dense]
+        launches = []
+        for b in seq:
+            got = eng.compute(b)
+            check(got, oracle.batch(b, threads=16), what="auto order")
+            launches.append(got.stats["kernel_launches"])
+        assert launches[1] > launches[0]                     # second dense batch: FP64-first chain (one more launch pair)
+        assert launches[3] < launches[2]                     # second sparse batch: back to FP32 first
+
+
+def test_use_double_switch(pkg, engine, oracle):
+    """phmm_options.use_double = the reference's g_use_double (intel_pairhmm.hpp:58,71,135): the FP32 pass is
+    skipped (raw FP32 = 0.0f), every pair is scored in FP64 and reported as rescued."""
+    b = pkg.Batch.concat([pkg.synth.random_small(21, n_regions=5, general_gaps=False), pkg.synth.s3(1, seed=3)])
+    want = oracle.batch(b, threads=16)
+    logd = np.log10(want_raw64(oracle, b)) - oracle.log10_init()[1]
+    with pkg.PairHMMEngine(devices=[0], use_double=True) as eng:
+        got = eng.compute(b)
+    assert got.rescued.all() and got.stats["n_rescued"] == b.n_pairs
+    assert not got.raw32.any()
+    assert _maxerr(got.log10, logd) <= TOL64
+    # where the FP32 path would NOT have been rescued the two precisions agree to FP32 accuracy
+    keep = ~want["rescued"].astype(bool)
+    assert _maxerr(got.log10[keep], want["log10"][keep]) <= 1e-4
+
+
+def want_raw64(oracle, b):
+    """FP64 forward sum of EVERY pair from the oracle (its batch() only keeps them for rescued pairs)."""
+    out = np.empty(b.n_pairs, np.float64)
+    ob = b.region_out_beg
+    for g in range(b.n_regions):
+        r0, r1 = int(b.region_read_beg[g]), int(b.region_read_beg[g + 1])
+        h0, h1 = int(b.region_hap_beg[g]), int(b.region_hap_beg[g + 1])
+        k = int(ob[g])
+        for r in range(r0, r1):
+            a, z = int(b.read_off[r]), int(b.read_off[r + 1])
+            for h in range(h0, h1):
+                c, d = int(b.hap_off[h]), int(b.hap_off[h + 1])
+                out[k] = oracle.forward(b.read_bases[a:z], b.read_q[a:z], b.read_i[a:z], b.read_d[a:z], b.read_c[a:z],
+                                        b.hap_bases[c:d], "f64")
+                k += 1
+    return out
+
+
 def test_pinned_inputs_upload_without_the_staging_copy(pkg, engine):
     """PHMM_BATCH_PINNED_INPUTS: the byte arrays go to the device straight from the caller's page-locked memory;
     same bits as the staged-copy path, through compute and through several tickets in flight, with constant
