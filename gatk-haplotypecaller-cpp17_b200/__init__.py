@@ -70,11 +70,21 @@ class _Result(C.Structure):
                 ("rescued", C.c_void_p), ("stats", Stats)]
 
 
+class _Sites(C.Structure):
+    _fields_ = [("n_sites", C.c_int32), ("site_region", C.c_void_p), ("site_n_alleles", C.c_void_p),
+                ("hap_allele", C.c_void_p), ("read_overlap", C.c_void_p)]
+
+
+class _GlResult(C.Structure):
+    _fields_ = [("genotype_lik", C.c_void_p), ("site_n_reads", C.c_void_p), ("read_keep", C.c_void_p),
+                ("capped_lik", C.c_void_p), ("stats", Stats)]
+
+
 EXPORTS = ["phmm_create", "phmm_destroy", "phmm_compute", "phmm_submit", "phmm_wait", "phmm_strerror",
            "phmm_last_error", "phmm_abi_version", "phmm_normalize_filter", "phmm_tables",
            "phmm_stage", "phmm_run_staged", "phmm_run_staged_ex", "phmm_run_staged_pipelined",
            "phmm_fetch_staged", "phmm_free_staged", "phmm_plan", "phmm_sw_align", "phmm_host_register",
-           "phmm_host_unregister", "phmm_host_alloc", "phmm_host_free"]
+           "phmm_host_unregister", "phmm_host_alloc", "phmm_host_free", "phmm_submit_gl", "phmm_wait_gl", "phmm_jacobian_table"]
 
 class _PlanInfo(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("mode", C.c_int32), ("n_jobs", C.c_int32), ("n_long_pairs", C.c_int32),
@@ -157,6 +167,9 @@ def lib():
         L.phmm_plan.argtypes = [C.POINTER(_Batch), C.c_int32, C.c_int32, C.POINTER(_PlanInfo), C.c_void_p, C.c_int64]
         L.phmm_host_register.argtypes = [C.c_void_p, C.c_size_t]
         L.phmm_host_unregister.argtypes = [C.c_void_p]
+        L.phmm_submit_gl.argtypes = [C.c_void_p, C.POINTER(_Batch), C.POINTER(_Sites), C.POINTER(C.c_int64)]
+        L.phmm_wait_gl.argtypes = [C.c_void_p, C.c_int64, C.POINTER(_GlResult)]
+        L.phmm_jacobian_table.argtypes = [C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.c_int32)]
         L.phmm_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
         L.phmm_host_free.argtypes = [C.c_void_p]
         L.phmm_sw_align.argtypes = [C.c_int32, C.POINTER(_SwBatch), C.POINTER(_SwResult)]
@@ -175,6 +188,60 @@ def host_tables():
     L.phmm_tables(C.byref(pf), C.byref(mf), C.byref(pd), C.byref(md), C.byref(n))
     return {"ph2pr_f32": np.ctypeslib.as_array(pf, (128,)).copy(), "mm_f32": np.ctypeslib.as_array(mf, (n.value,)).copy(),
             "ph2pr_f64": np.ctypeslib.as_array(pd, (128,)).copy(), "mm_f64": np.ctypeslib.as_array(md, (n.value,)).copy()}
+
+
+def jacobian_table():
+    """hc::MathUtils' Jacobian-logarithm table as the library holds it (utils/math_utils.hpp:17-29)."""
+    t, n = C.POINTER(C.c_double)(), C.c_int32()
+    lib().phmm_jacobian_table(C.byref(t), C.byref(n))
+    return np.ctypeslib.as_array(t, (n.value,)).copy()
+
+
+class Sites:
+    """Variant sites of a batch for the device-side genotype reduction (phmm_sites of include/phmm.h).
+    per_site: list of (region, n_alleles, hap_allele uint8[n_haps(region)], read_overlap uint8[n_reads(region)] or None),
+    regions non-decreasing.  If any site gives no overlap array, every read is taken to overlap every site."""
+
+    def __init__(self, batch, per_site):
+        self.n_sites = len(per_site)
+        self.site_region = np.ascontiguousarray([p[0] for p in per_site], np.int32)
+        self.site_n_alleles = np.ascontiguousarray([p[1] for p in per_site], np.int32)
+        cat = lambda xs: np.ascontiguousarray(np.concatenate(xs), np.uint8) if xs else np.zeros(0, np.uint8)
+        self.hap_allele = cat([np.asarray(p[2], np.uint8) for p in per_site])
+        self.has_overlap = bool(per_site) and all(p[3] is not None for p in per_site)
+        self.read_overlap = cat([np.asarray(p[3], np.uint8) for p in per_site]) if self.has_overlap else None
+        nh, nr = batch.haps_per_region, batch.reads_per_region
+        assert len(self.hap_allele) == int(nh[self.site_region].sum()) if self.n_sites else True
+        if self.has_overlap:
+            assert len(self.read_overlap) == int(nr[self.site_region].sum())
+        self.gl_off = np.concatenate([[0], np.cumsum(self.site_n_alleles.astype(np.int64) * (self.site_n_alleles + 1) // 2)]).astype(np.int64)
+
+    def c_struct(self):
+        p = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
+        s = _Sites()
+        s.n_sites = self.n_sites
+        s.site_region, s.site_n_alleles, s.hap_allele = p(self.site_region), p(self.site_n_alleles), p(self.hap_allele)
+        s.read_overlap = p(self.read_overlap) if self.has_overlap else None
+        return s
+
+
+class GlResult:
+    def __init__(self, batch, sites, want_matrix=False):
+        self.gl = np.zeros(int(sites.gl_off[-1]), np.float64)
+        self.gl_off = sites.gl_off
+        self.site_n_reads = np.zeros(sites.n_sites, np.int32)
+        self.read_keep = np.zeros(batch.n_reads, np.uint8)
+        self.capped = np.zeros(batch.n_pairs, np.float64) if want_matrix else None
+        self._c = _GlResult()
+        p = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+        self._c.genotype_lik, self._c.site_n_reads, self._c.read_keep, self._c.capped_lik = p(self.gl), p(self.site_n_reads), p(self.read_keep), p(self.capped)
+
+    def site(self, k):
+        return self.gl[int(self.gl_off[k]):int(self.gl_off[k + 1])]
+
+    @property
+    def stats(self):
+        return self._c.stats.as_dict()
 
 
 class Batch:
@@ -434,6 +501,20 @@ class PairHMMEngine:
         res = result if result is not None else Result(n, want_raw)
         self._check(self._L.phmm_wait(self._h, ticket, C.byref(res._c)))
         return res
+
+    # -- device-side genotype reduction: phmm_submit_gl / phmm_wait_gl
+    def submit_gl(self, batch, sites):
+        t = C.c_int64()
+        cb, cs = batch.c_struct(), sites.c_struct()
+        self._check(self._L.phmm_submit_gl(self._h, C.byref(cb), C.byref(cs), C.byref(t)))
+        return t.value
+
+    def wait_gl(self, ticket, result):
+        self._check(self._L.phmm_wait_gl(self._h, ticket, C.byref(result._c)))
+        return result
+
+    def compute_gl(self, batch, sites, want_matrix=False):
+        return self.wait_gl(self.submit_gl(batch, sites), GlResult(batch, sites, want_matrix))
 
     # -- device-resident form
     def stage(self, batch):

@@ -208,6 +208,7 @@ struct Part {
     int g0 = 0, g1 = 0;                       // region range in the caller's batch
     int n_regions = 0, n_reads = 0, n_haps = 0;
     int64_t n_pairs = 0, n_cells = 0, out0 = 0;   // out0: offset of this part in the batch output
+    int read0 = 0;                            // first read of the part in the caller's batch
     int mode = kModeGeneral;                 // kernel MODE: general / batch-constant gaps / constant with i == d
     uint8_t gap[3] = {0, 0, 0};              // the batch-constant (i, d, c) bytes when mode != general
     int max_H = 0, max_nh = 0;
@@ -235,6 +236,9 @@ struct Slot {
     PinnedBuf h_in, h_jobs, h_out, h_rescue;
     DeviceBuf d_in, d_jobs, d_out, d_rescue, d_flags, d_work;
     int sm_count = 148;
+    bool device_log10 = false;               // d_out = [16 B header | lik32[n_pad] | raw32[n_pad]]; the D2H takes header + lik32
+                                             // (device_log10) or everything (host log10f pass)
+    float log10_init_f = 0.f;
     int async_rc = PHMM_OK;                  // failure after the submitter was released: reported by phmm_wait
     std::string async_err;
     struct StageCtx {                        // what the pack phase hands to the plan + launch phase
@@ -243,10 +247,26 @@ struct Slot {
         phmm_batch view{};                   // the part as a batch of its own, over the packed copy
         bool general = false, empty = true;
         bool zero_copy = false;              // PHMM_BATCH_PINNED_INPUTS: byte arrays upload from the caller's memory
-        int g0 = 0, g1 = 0;
+        int g0 = 0, g1 = 0, read0 = 0;
         int64_t out0 = 0;
         std::chrono::steady_clock::time_point t_begin, t_packed;
     } stage;
+    // device-side genotype reduction (phmm_submit_gl): the part's sites and its outputs
+    struct GlCtx {
+        bool on = false;
+        int s0 = 0, s1 = 0;                      // site range of the part in the caller's arrays
+        int64_t gl0 = 0, n_gl = 0;               // genotype-likelihood range
+        int64_t n_site_reads = 0, n_site_haps = 0;
+        // what the submitter hands to the pack phase (valid until the pack phase is over)
+        const phmm_sites* sites = nullptr;
+        const int64_t* site_hap_off = nullptr; const int64_t* site_read_off = nullptr; const int64_t* gl_off = nullptr;
+        size_t o_region = 0, o_alleles = 0, o_hap_off = 0, o_read_off = 0, o_gl_off = 0, o_hap_allele = 0, o_overlap = 0, bytes = 0;
+        bool has_overlap = false;
+        GenotypeArgs args{};
+        size_t out_gl = 0, out_nused = 0, out_keep = 0, out_bytes = 0;      // layout of the output block
+    } gl;
+    PinnedBuf h_sites, h_gl;
+    DeviceBuf d_sites, d_gl_out, d_lik64, d_gl_scratch;
     bool busy = false;
     Part part;
     KernelArgs args{};
@@ -260,11 +280,14 @@ struct DeviceCtx {
     int sm_count = 148;
     float last_rescue_frac = 0.f;        // share of pairs the previous batch redid in FP64
     int fp64_first_opt = 0;              // phmm_options.fp64_first
+    bool device_log10 = false;           // phmm_engine::device_log10
     std::unique_ptr<HostPool> pool;      // host_threads - 1 helpers for this device's worker thread
     std::vector<Slot> slots;
     int next_slot = 0;
     float* d_ph2pr_f = nullptr; float* d_mm_f = nullptr;
     double* d_ph2pr_d = nullptr; double* d_mm_d = nullptr;
+    double* d_jacobian = nullptr;        // hc::MathUtils' Jacobian table, uploaded by the first phmm_submit_gl part
+    std::once_flag jacobian_once;
     // Two threads per device.  The WORKER plans, launches and finalizes (and serves the staged form); the
     // PACKER only copies a submitter's arrays into pinned staging and starts their upload, so that a
     // submitter is never held up behind the planning or the log10 pass of an earlier batch.
@@ -313,6 +336,7 @@ struct Latch {
 struct TicketRec {
     std::vector<std::pair<int, int>> parts;   // (device index, slot index)
     int64_t n_pairs = 0;
+    bool gl = false;                          // a phmm_submit_gl ticket: waited with phmm_wait_gl
     std::chrono::steady_clock::time_point t0;
 };
 
@@ -326,6 +350,7 @@ struct phmm_engine {
     std::map<phmm_ticket, TicketRec> tickets;
     phmm_ticket next_ticket = 1;
     int host_threads = 1;
+    bool device_log10 = false;           // final float log10 on the device (phmm_finalize.cu); false: host log10f pass
 
     void set_error(const std::string& s) { std::lock_guard<std::mutex> lk(mu); last_error = s; }
 };
@@ -464,7 +489,8 @@ int launch_kernels(Slot& s, bool exact, int tier_lo, int tier_hi, std::string& e
     if (normal_pass) {
         p.launches = 0;
         s.k32_valid = false;
-        CUDA_TRY(cudaMemsetAsync(s.d_out.p, 0, skip32 ? 16 + sizeof(float) * (size_t)p.n_pairs : 16, s.stream));
+        CUDA_TRY(cudaMemsetAsync(s.d_out.p, 0, 16, s.stream));                        // counters
+        if (skip32) CUDA_TRY(cudaMemsetAsync(a.raw32, 0, sizeof(float) * (size_t)p.n_pairs, s.stream));   // every raw FP32 sum is 0.0f
         CUDA_TRY(cudaMemsetAsync(flags_base, 0, kWorkHeaderBytes, s.stream));
         CUDA_TRY(cudaMemsetAsync(flags_base + kWorkHeaderBytes, skip32 ? 1 : 0, (size_t)p.n_jobs * p.hap_chunks, s.stream));
         CUDA_TRY(cudaEventRecord(s.ev_k0, s.stream));
@@ -476,10 +502,26 @@ int launch_kernels(Slot& s, bool exact, int tier_lo, int tier_hi, std::string& e
     if (fork) CUDA_TRY(cudaEventRecord(s.ev_fork, s.stream));
     int which = 0;
     const int subs64 = (p.haps_per_job + p.haps_per_job64 - 1) / p.haps_per_job64;    // FP64 items per FP32 unit
-    size_t work_off = 0;                                     // in uint2 items: every slot owns [FP64 list | FP32 list]
-    for (int k = 0; k < 2 * kNumShapes; k++) {
+    // Launch order: the kernel slot with the most work first.  Chains on different streams run side by side only
+    // where the chip has room, so the small grids of a ragged batch end up filling the tail of the big one --
+    // launched last (slot order), the big grid drained alone instead (8% of the ragged window stream).
+    int order[2 * kNumShapes];
+    size_t slot_off[2 * kNumShapes];
+    {
+        size_t off = 0;                                      // in uint2 items: every slot owns [FP64 list | FP32 list]
+        for (int k = 0; k < 2 * kNumShapes; k++) {
+            order[k] = k;
+            slot_off[k] = off;
+            off += (size_t)(p.job_beg[k + 1] - p.job_beg[k]) * p.hap_chunks * (subs64 + 1);
+        }
+        auto work = [&](int k) { return (int64_t)(p.job_beg[k + 1] - p.job_beg[k]) * kShapes[k % kNumShapes].K * 32; };
+        std::stable_sort(order, order + 2 * kNumShapes, [&](int x, int y) { return work(x) > work(y); });
+    }
+    for (int oi = 0; oi < 2 * kNumShapes; oi++) {
+        const int k = order[oi];
         const int n = p.job_beg[k + 1] - p.job_beg[k];
         if (n == 0) continue;
+        const size_t work_off = slot_off[k];
         cudaStream_t st = s.stream;
         if (fork) {
             const int ai = which++ % kAuxStreams;
@@ -491,7 +533,6 @@ int launch_kernels(Slot& s, bool exact, int tier_lo, int tier_hi, std::string& e
         const size_t cap64 = (size_t)n * p.hap_chunks * subs64, cap32 = (size_t)n * p.hap_chunks;
         uint2* const list64 = (uint2*)s.d_work.p + work_off;
         uint2* const list32 = list64 + cap64;
-        work_off += cap64 + cap32;
         unsigned* const cnt = counters + 4 * k;              // {count64, cursor64, count32, cursor32}
         KernelArgs ak = a;
         ak.jobs = a.jobs + p.job_beg[k];
@@ -554,6 +595,12 @@ int launch_kernels(Slot& s, bool exact, int tier_lo, int tier_hi, std::string& e
     if (normal_pass) {
         if (p.n_long) {      // reads beyond one lane-group pass: all precision tiers inside one launch
             launch_long_reads(a, s.d_long, p.n_long, p.mode == kModeGeneral, exact, use_double, s.stream);
+            CUDA_TRY(cudaGetLastError());
+            p.launches++;
+        }
+        if (s.device_log10) {                                // raw sums -> final float log10 values + counters
+            launch_finalize(a.raw32, p.n_pairs, s.log10_init_f, (float*)((uint8_t*)s.d_out.p + 16), (unsigned*)s.d_out.p,
+                            s.sm_count, s.stream);
             CUDA_TRY(cudaGetLastError());
             p.launches++;
         }
@@ -839,8 +886,15 @@ int stage_pack(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1, int6
     const int h0 = b->region_hap_beg[g0], h1 = b->region_hap_beg[g1];
     const int n_reads = r1 - r0, n_haps = h1 - h0, n_regions = g1 - g0;
     p.n_reads = n_reads; p.n_haps = n_haps;
+    p.read0 = c.read0 = r0;
     p.n_pairs = batch_pairs(b, g0, g1);
-    if (p.n_pairs == 0) return PHMM_OK;
+    if (p.n_pairs == 0) {
+        if (s.gl.on) {                                        // sums over zero reads: finalize_part_gl writes them
+            s.gl.gl0 = s.gl.gl_off[s.gl.s0]; s.gl.n_gl = s.gl.gl_off[s.gl.s1] - s.gl.gl0;
+            s.gl.sites = nullptr; s.gl.site_hap_off = s.gl.site_read_off = s.gl.gl_off = nullptr;
+        }
+        return PHMM_OK;
+    }
     c.empty = false;
     const int rb0 = b->read_off[r0], rb1 = b->read_off[r1];
     const int hb0 = b->hap_off[h0], hb1 = b->hap_off[h1];
@@ -926,7 +980,44 @@ int stage_pack(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1, int6
     view.hap_off = (const int32_t*)(hp + o_hap_off);
     view.hap_bases = zero_copy ? b->hap_bases + hb0 : hp + o_haps;
     view.gap_open_i = gap[0]; view.gap_open_d = gap[1]; view.gap_cont_c = gap[2];
+    if (s.gl.on) {
+        // the part's sites: rebased index arrays + the haplotype -> allele and read-overlap bytes, one pinned block
+        Slot::GlCtx& q = s.gl;
+        const phmm_sites* S = q.sites;
+        const int ns = q.s1 - q.s0;
+        const int64_t hap0 = q.site_hap_off[q.s0], read0 = q.site_read_off[q.s0];
+        q.n_site_haps = q.site_hap_off[q.s1] - hap0;
+        q.n_site_reads = q.site_read_off[q.s1] - read0;
+        q.gl0 = q.gl_off[q.s0]; q.n_gl = q.gl_off[q.s1] - q.gl0;
+        q.has_overlap = S->read_overlap != nullptr;
+        size_t o = 0;
+        auto take2 = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes); return at; };
+        q.o_region = take2(sizeof(int32_t) * (size_t)ns);
+        q.o_alleles = take2(sizeof(int32_t) * (size_t)ns);
+        q.o_hap_off = take2(sizeof(int64_t) * (size_t)(ns + 1));
+        q.o_read_off = take2(sizeof(int64_t) * (size_t)(ns + 1));
+        q.o_gl_off = take2(sizeof(int64_t) * (size_t)(ns + 1));
+        q.o_hap_allele = take2((size_t)q.n_site_haps);
+        q.o_overlap = take2(q.has_overlap ? (size_t)q.n_site_reads : 0);
+        q.bytes = o;
+        CUDA_TRY(s.h_sites.reserve(q.bytes + 16));
+        CUDA_TRY(s.d_sites.reserve(q.bytes + 16));
+        uint8_t* hs = (uint8_t*)s.h_sites.p;
+        for (int k = 0; k < ns; k++) {
+            ((int32_t*)(hs + q.o_region))[k] = S->site_region[q.s0 + k] - g0;
+            ((int32_t*)(hs + q.o_alleles))[k] = S->site_n_alleles[q.s0 + k];
+        }
+        for (int k = 0; k <= ns; k++) {
+            ((int64_t*)(hs + q.o_hap_off))[k] = q.site_hap_off[q.s0 + k] - hap0;
+            ((int64_t*)(hs + q.o_read_off))[k] = q.site_read_off[q.s0 + k] - read0;
+            ((int64_t*)(hs + q.o_gl_off))[k] = q.gl_off[q.s0 + k] - q.gl0;
+        }
+        if (q.n_site_haps) std::memcpy(hs + q.o_hap_allele, S->hap_allele + hap0, (size_t)q.n_site_haps);
+        if (q.has_overlap && q.n_site_reads) std::memcpy(hs + q.o_overlap, S->read_overlap + read0, (size_t)q.n_site_reads);
+        q.sites = nullptr; q.site_hap_off = q.site_read_off = q.gl_off = nullptr;     // the caller's arrays are not touched again
+    }
     c.t_packed = std::chrono::steady_clock::now();
+    if (s.gl.on && s.gl.bytes) CUDA_TRY(cudaMemcpyAsync(s.d_sites.p, s.h_sites.p, s.gl.bytes, cudaMemcpyHostToDevice, s.stream));
     if (!zero_copy) CUDA_TRY(cudaMemcpyAsync(s.d_in.p, s.h_in.p, in_bytes, cudaMemcpyHostToDevice, s.stream));
     else {
         uint8_t* dpz = (uint8_t*)s.d_in.p;
@@ -943,8 +1034,11 @@ int stage_pack(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1, int6
     return PHMM_OK;                       // the submitter's arrays are no longer needed (zero copy: only the index arrays)
 }
 
+int launch_genotype_part(DeviceCtx& dc, Slot& s, std::string& err);
+
 int stage_launch(DeviceCtx& dc, Slot& s, bool exact, bool use_double, bool do_launch, std::string& err)
 {
+    s.device_log10 = dc.device_log10;
     static const bool trace = getenv("PHMM_TRACE") != nullptr;      // development aid: host time per phase
     Slot::StageCtx& c = s.stage;
     if (c.empty) return PHMM_OK;
@@ -963,7 +1057,7 @@ int stage_launch(DeviceCtx& dc, Slot& s, bool exact, bool use_double, bool do_la
     {
         int rcp = plan_part(&view, 0, n_regions, out0, dc.sm_count, dc.last_rescue_frac, pool, p, plan, err, dc.fp64_first_opt);
         if (rcp) return rcp;
-        p.g0 = g0; p.g1 = g1; p.out0 = out0;
+        p.g0 = g0; p.g1 = g1; p.out0 = out0; p.read0 = c.read0;
     }
     const std::vector<LongPair>& long_pairs = plan.long_pairs;
     const std::vector<WarpJob>* jobs_k = plan.jobs_k;
@@ -973,9 +1067,11 @@ int stage_launch(DeviceCtx& dc, Slot& s, bool exact, bool use_double, bool do_la
     const size_t jobs_bytes = o_long + sizeof(LongPair) * long_pairs.size();
     CUDA_TRY(s.h_jobs.reserve(jobs_bytes + 16));
     CUDA_TRY(s.d_jobs.reserve(jobs_bytes + 16));
-    const size_t out_bytes = 16 + sizeof(float) * (size_t)p.n_pairs;
-    CUDA_TRY(s.h_out.reserve(out_bytes));
-    CUDA_TRY(s.d_out.reserve(out_bytes));
+    const size_t n_pad = ((size_t)p.n_pairs + 3) / 4 * 4;
+    const size_t out_bytes_all = 16 + 2 * sizeof(float) * n_pad;
+    const size_t out_bytes = s.device_log10 ? 16 + sizeof(float) * (size_t)p.n_pairs : out_bytes_all;   // what the D2H moves
+    CUDA_TRY(s.h_out.reserve(out_bytes_all));
+    CUDA_TRY(s.d_out.reserve(out_bytes_all));
     CUDA_TRY(s.d_rescue.reserve(sizeof(RescueOut) * (size_t)p.n_pairs));
     CUDA_TRY(s.d_flags.reserve(kWorkHeaderBytes + (size_t)p.n_jobs * p.hap_chunks + 16));
     {   // work lists: per job and FP32 chunk one FP32 item and ceil(hpj / hpj64) FP64 items (launch_kernels)
@@ -983,6 +1079,7 @@ int stage_launch(DeviceCtx& dc, Slot& s, bool exact, bool use_double, bool do_la
         CUDA_TRY(s.d_work.reserve(sizeof(uint2) * ((size_t)p.n_jobs * p.hap_chunks * (subs64 + 1) + 16)));
     }
     s.sm_count = dc.sm_count;
+    s.log10_init_f = host_tables().log10_init_f;
     {
         uint8_t* hj = (uint8_t*)s.h_jobs.p;
         if (!long_pairs.empty()) std::memcpy(hj + o_long, long_pairs.data(), sizeof(LongPair) * long_pairs.size());
@@ -1023,27 +1120,87 @@ int stage_launch(DeviceCtx& dc, Slot& s, bool exact, bool use_double, bool do_la
     a.stream_cap = (int32_t)((2 * (kSkew * 31 + 3) + (size_t)p.haps_per_job * (p.max_H + 2) + 127) / 128 * 128);
     a.smem_bytes_per_warp = 0;    // set per shape at launch (the prior tables depend on K and G)
     a.rescue_count = (unsigned*)s.d_out.p;
-    a.raw32 = (float*)((uint8_t*)s.d_out.p + 16);
+    a.raw32 = (float*)((uint8_t*)s.d_out.p + 16) + n_pad;
     a.rescue_out = (RescueOut*)s.d_rescue.p;
     a.job_flags = (uint8_t*)s.d_flags.p + kWorkHeaderBytes;
     a.job_flag_base = 0;
     a.work_in = nullptr; a.work_in_count = nullptr; a.work_in_cursor = nullptr; a.first64 = 0;
 
     if (jobs_bytes) CUDA_TRY(cudaMemcpyAsync(s.d_jobs.p, s.h_jobs.p, jobs_bytes, cudaMemcpyHostToDevice, s.stream));
-    p.h2d_bytes = in_bytes + jobs_bytes;
+    p.h2d_bytes = in_bytes + jobs_bytes + (s.gl.on ? s.gl.bytes : 0);
     if (!do_launch) return PHMM_OK;
 
     int rc = launch_kernels(s, exact, 1, 2, err, use_double);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(s.h_out.p, s.d_out.p, out_bytes, cudaMemcpyDeviceToHost, s.stream));
+    if (s.gl.on) {
+        // genotype reduction on the device: the matrix stays here, only the counters and the per-site vectors go back
+        rc = launch_genotype_part(dc, s, err);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(s.h_out.p, s.d_out.p, 16, cudaMemcpyDeviceToHost, s.stream));
+        p.d2h_bytes = 16 + s.gl.out_bytes;
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(s.h_out.p, s.d_out.p, out_bytes, cudaMemcpyDeviceToHost, s.stream));
+        p.d2h_bytes = out_bytes;
+    }
     CUDA_TRY(cudaEventRecord(s.ev_done, s.stream));
-    p.d2h_bytes = out_bytes;
     if (trace) {
         const auto t_end = std::chrono::steady_clock::now();
         auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
         fprintf(stderr, "phmm trace: stage pack %.3f ms | plan %.3f ms, launch %.3f ms (%d jobs, %d launches, %lld pairs)\n",
                 ms(t_begin, t_packed), ms(t_packed, t_planned), ms(t_planned, t_end), p.n_jobs, p.launches, (long long)p.n_pairs);
     }
+    return PHMM_OK;
+}
+
+// Device-side genotype reduction of a staged slot (phmm_genotype.cu) and the download of its (small) outputs.
+int launch_genotype_part(DeviceCtx& dc, Slot& s, std::string& err)
+{
+    Slot::GlCtx& q = s.gl;
+    Part& p = s.part;
+    const int ns = q.s1 - q.s0;
+    std::call_once(dc.jacobian_once, [&] {
+        int n = 0;
+        const double* t = jacobian_table(&n);
+        if (cudaMalloc(&dc.d_jacobian, sizeof(double) * (size_t)n) == cudaSuccess)
+            cudaMemcpy(dc.d_jacobian, t, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice);
+        else dc.d_jacobian = nullptr;
+    });
+    if (!dc.d_jacobian) { err = "cannot upload the Jacobian table"; return PHMM_ERR_OOM; }
+    CUDA_TRY(s.d_lik64.reserve(sizeof(double) * (size_t)p.n_pairs + 16));
+    CUDA_TRY(s.d_gl_scratch.reserve((size_t)q.n_site_reads * (8 * sizeof(double) + 1) + 256));
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes); return at; };
+    q.out_gl = take(sizeof(double) * (size_t)q.n_gl);
+    q.out_nused = take(sizeof(int32_t) * (size_t)ns);
+    q.out_keep = take((size_t)p.n_reads);
+    q.out_bytes = o;
+    CUDA_TRY(s.d_gl_out.reserve(q.out_bytes + 16));
+    CUDA_TRY(s.h_gl.reserve(q.out_bytes + 16));
+    const uint8_t* ds = (const uint8_t*)s.d_sites.p;
+    uint8_t* dout = (uint8_t*)s.d_gl_out.p;
+    GenotypeArgs& g = q.args;
+    g.lik64 = (double*)s.d_lik64.p;
+    g.n_pairs = p.n_pairs; g.n_regions = p.n_regions; g.n_reads = p.n_reads; g.n_sites = ns;
+    g.region_read_beg = s.args.region_read_beg; g.region_hap_beg = s.args.region_hap_beg;
+    g.region_out_beg = s.args.region_out_beg; g.read_off = s.args.read_off;
+    g.read_keep = dout + q.out_keep;
+    g.site_region = (const int32_t*)(ds + q.o_region); g.site_n_alleles = (const int32_t*)(ds + q.o_alleles);
+    g.site_hap_off = (const int64_t*)(ds + q.o_hap_off); g.hap_allele = ds + q.o_hap_allele;
+    g.site_read_off = (const int64_t*)(ds + q.o_read_off); g.read_overlap = q.has_overlap ? ds + q.o_overlap : nullptr;
+    g.gl_off = (const int64_t*)(ds + q.o_gl_off);
+    g.scratch_al = (double*)s.d_gl_scratch.p;
+    g.scratch_used = (uint8_t*)s.d_gl_scratch.p + (size_t)q.n_site_reads * 8 * sizeof(double);
+    g.gl = (double*)(dout + q.out_gl); g.site_n_used = (int32_t*)(dout + q.out_nused);
+    g.jacobian = dc.d_jacobian;
+    g.inv_step = 1.0 / 0.0001;                               // JacobianLogTable::INV_STEP, math_utils.hpp:23
+    g.log10_2 = std::log10(2.0);                             // genotyper.hpp:280, :316 (the host's libm, as the reference's)
+    const size_t n_pad = ((size_t)p.n_pairs + 3) / 4 * 4;
+    (void)n_pad;
+    launch_genotype(g, (const float*)((const uint8_t*)s.d_out.p + 16), (const RescueOut*)s.d_rescue.p, (const unsigned*)s.d_out.p,
+                    host_tables().log10_init_d, s.sm_count, s.stream);
+    CUDA_TRY(cudaGetLastError());
+    p.launches += 4;
+    CUDA_TRY(cudaMemcpyAsync(s.h_gl.p, s.d_gl_out.p, q.out_bytes, cudaMemcpyDeviceToHost, s.stream));
     return PHMM_OK;
 }
 
@@ -1069,8 +1226,11 @@ int finalize_part(phmm_engine* e, DeviceCtx& dc, Slot& s, phmm_result* r, std::s
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1));
     p.kernel_ms = ms;
-    unsigned count = *(const unsigned*)s.h_out.p;
-    const float* raw32 = (const float*)((const uint8_t*)s.h_out.p + 16);
+    const unsigned* header = (const unsigned*)s.h_out.p;     // {rescue_count, marked, underflowed, unscored}
+    unsigned count = header[0];
+    const size_t n_pad = ((size_t)p.n_pairs + 3) / 4 * 4;
+    const float* lik32 = (const float*)((const uint8_t*)s.h_out.p + 16);
+    const float* raw32 = lik32 + n_pad;
     if (count > (uint64_t)p.n_pairs) { err = "rescue counter overflow"; return PHMM_ERR_CUDA; }
     const Tables& T = host_tables();
     double* out = r->log10_lik + p.out0;
@@ -1079,21 +1239,40 @@ int finalize_part(phmm_engine* e, DeviceCtx& dc, Slot& s, phmm_result* r, std::s
     uint8_t* ores = r->rescued ? r->rescued + p.out0 : nullptr;
     const float log10_init_f = T.log10_init_f;
     std::atomic<int64_t> need_rescue{0}, marked{0}, unscored{0};
-    auto body = [&](int64_t i0, int64_t i1) {
-        int64_t nr = 0, nm = 0, bad = 0;
-        for (int64_t i = i0; i < i1; i++) {
-            const float f = raw32[i];
-            if (f != f) { bad++; out[i] = std::nan(""); }           // an FP64-first pair the FP32 pass never scored: a bug
-            else if (f < kMinAccepted) { nr++; nm += std::signbit(f); out[i] = std::nan(""); }
-            else out[i] = (double)(log10f(f) - log10_init_f);       // float subtraction, :142
-            if (o32) o32[i] = std::fabs(f);     // the sign bit only marks pairs for the flush-exact FP64 tier
-            if (o64) o64[i] = 0.0;
-            if (ores) ores[i] = 0;
-        }
-        need_rescue += nr; marked += nm; unscored += bad;
-    };
     const int nt = (int)std::min<int64_t>(dc.pool->width(), std::max<int64_t>(1, p.n_pairs / 16384));
-    dc.pool->parallel_for(nt, [&](int t) { body(p.n_pairs * t / nt, p.n_pairs * (t + 1) / nt); });
+    if (s.device_log10) {
+        // the device took the log10 (phmm_finalize.cu); what is left is widening floats.  Raw FP32 sums come over
+        // only when the caller asks for them.
+        marked = header[1]; need_rescue = header[2]; unscored = header[3];
+        if (o32) {
+            CUDA_TRY(cudaMemcpyAsync((void*)raw32, (const uint8_t*)s.d_out.p + 16 + sizeof(float) * n_pad, sizeof(float) * (size_t)p.n_pairs,
+                                     cudaMemcpyDeviceToHost, s.stream));
+            CUDA_TRY(cudaStreamSynchronize(s.stream));
+            p.d2h_bytes += sizeof(float) * (size_t)p.n_pairs;
+        }
+        auto body = [&](int64_t i0, int64_t i1) {
+            for (int64_t i = i0; i < i1; i++) out[i] = (double)lik32[i];        // NaN where the FP64 result goes
+            if (o32) for (int64_t i = i0; i < i1; i++) o32[i] = std::fabs(raw32[i]);
+            if (o64) std::memset(o64 + i0, 0, sizeof(double) * (size_t)(i1 - i0));
+            if (ores) std::memset(ores + i0, 0, (size_t)(i1 - i0));
+        };
+        dc.pool->parallel_for(nt, [&](int t) { body(p.n_pairs * t / nt, p.n_pairs * (t + 1) / nt); });
+    } else {
+        auto body = [&](int64_t i0, int64_t i1) {
+            int64_t nr = 0, nm = 0, bad = 0;
+            for (int64_t i = i0; i < i1; i++) {
+                const float f = raw32[i];
+                if (f != f) { bad++; out[i] = std::nan(""); }           // an FP64-first pair the FP32 pass never scored: a bug
+                else if (f < kMinAccepted) { nr++; nm += std::signbit(f); out[i] = std::nan(""); }
+                else out[i] = (double)(log10f(f) - log10_init_f);       // float subtraction, :142
+                if (o32) o32[i] = std::fabs(f);     // the sign bit only marks pairs for the flush-exact FP64 tier
+                if (o64) o64[i] = 0.0;
+                if (ores) ores[i] = 0;
+            }
+            need_rescue += nr; marked += nm; unscored += bad;
+        };
+        dc.pool->parallel_for(nt, [&](int t) { body(p.n_pairs * t / nt, p.n_pairs * (t + 1) / nt); });
+    }
     if (unscored.load()) { err = std::to_string(unscored.load()) + " pairs left unscored by the FP32 pass"; return PHMM_ERR_CUDA; }
     if (marked.load()) {
         // tier 3: pairs whose FP64 sum came out within reach of the denormal range are redone by the
@@ -1134,6 +1313,55 @@ int finalize_part(phmm_engine* e, DeviceCtx& dc, Slot& s, phmm_result* r, std::s
         auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
         fprintf(stderr, "phmm trace: finalize wait %.3f ms, log10 + rescue %.3f ms (kernels %.3f ms)\n",
                 ms(t_begin, t_synced), ms(t_synced, t_end), p.kernel_ms);
+    }
+    return PHMM_OK;
+}
+
+// phmm_wait_gl, one part: wait for the slot, run the flush-exact tier if a pair asked for it (and then the reduction
+// again), hand the per-site vectors to the caller.
+int finalize_part_gl(phmm_engine* e, DeviceCtx& dc, Slot& s, phmm_gl_result* r, std::string& err)
+{
+    Part& p = s.part;
+    Slot::GlCtx& q = s.gl;
+    const int ns = q.s1 - q.s0;
+    if (s.async_rc) { err = s.async_err; return s.async_rc; }
+    if (p.n_pairs == 0) {                                     // no pairs: every sum is over zero reads
+        for (int64_t k = 0; k < q.n_gl; k++) r->genotype_lik[q.gl0 + k] = 0.0;
+        if (r->site_n_reads) for (int k = 0; k < ns; k++) r->site_n_reads[q.s0 + k] = 0;
+        if (r->read_keep) std::memset(r->read_keep + p.read0, 1, (size_t)p.n_reads);
+        return PHMM_OK;
+    }
+    CUDA_TRY(cudaEventSynchronize(s.ev_done));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1));
+    p.kernel_ms = ms;
+    const unsigned* header = (const unsigned*)s.h_out.p;      // {rescue_count, marked, underflowed, unscored}
+    unsigned count = header[0];
+    if (header[3]) { err = std::to_string(header[3]) + " pairs left unscored by the FP32 pass"; return PHMM_ERR_CUDA; }
+    if (header[1]) {                                          // tier 3, then the reduction again over the patched matrix
+        int rc3 = launch_kernels(s, e->opt.exact_fp32 != 0, 3, 3, err);
+        if (rc3) return rc3;
+        rc3 = launch_genotype_part(dc, s, err);
+        if (rc3) return rc3;
+        CUDA_TRY(cudaMemcpyAsync(s.h_out.p, s.d_out.p, 16, cudaMemcpyDeviceToHost, s.stream));
+        CUDA_TRY(cudaStreamSynchronize(s.stream));
+        count = header[0];
+        p.d2h_bytes += 16 + q.out_bytes;
+    }
+    if (count != header[2]) {
+        err = "rescue list size " + std::to_string(count) + " != FP32 underflows " + std::to_string(header[2]);
+        return PHMM_ERR_CUDA;
+    }
+    p.rescue_count = count;
+    dc.last_rescue_frac = (float)((double)count / (double)p.n_pairs);
+    const uint8_t* ho = (const uint8_t*)s.h_gl.p;
+    std::memcpy(r->genotype_lik + q.gl0, ho + q.out_gl, sizeof(double) * (size_t)q.n_gl);
+    if (r->site_n_reads) std::memcpy(r->site_n_reads + q.s0, ho + q.out_nused, sizeof(int32_t) * (size_t)ns);
+    if (r->read_keep) std::memcpy(r->read_keep + p.read0, ho + q.out_keep, (size_t)p.n_reads);
+    if (r->capped_lik) {                                      // the matrix after all, on request (tests, hybrid callers)
+        CUDA_TRY(cudaMemcpyAsync(r->capped_lik + p.out0, s.d_lik64.p, sizeof(double) * (size_t)p.n_pairs, cudaMemcpyDeviceToHost, s.stream));
+        CUDA_TRY(cudaStreamSynchronize(s.stream));
+        p.d2h_bytes += sizeof(double) * (size_t)p.n_pairs;
     }
     return PHMM_OK;
 }
@@ -1181,6 +1409,7 @@ void free_slot(Slot& s)
 {
     s.h_in.release(); s.h_jobs.release(); s.h_out.release(); s.h_rescue.release();
     s.d_in.release(); s.d_jobs.release(); s.d_out.release(); s.d_rescue.release(); s.d_flags.release(); s.d_work.release();
+    s.h_sites.release(); s.h_gl.release(); s.d_sites.release(); s.d_gl_out.release(); s.d_lik64.release(); s.d_gl_scratch.release();
     for (int i = 0; i < kAuxStreams; i++) {
         if (s.ev_join[i]) cudaEventDestroy(s.ev_join[i]);
         if (s.aux[i]) cudaStreamDestroy(s.aux[i]);
@@ -1348,8 +1577,8 @@ static void teardown_device(DeviceCtx& dc)
     cudaSetDevice(dc.ordinal);
     for (auto& s : dc.slots) { if (s.stream) cudaStreamSynchronize(s.stream); free_slot(s); }
     dc.slots.clear();
-    cudaFree(dc.d_ph2pr_f); cudaFree(dc.d_mm_f); cudaFree(dc.d_ph2pr_d); cudaFree(dc.d_mm_d);
-    dc.d_ph2pr_f = dc.d_mm_f = nullptr; dc.d_ph2pr_d = dc.d_mm_d = nullptr;
+    cudaFree(dc.d_ph2pr_f); cudaFree(dc.d_mm_f); cudaFree(dc.d_ph2pr_d); cudaFree(dc.d_mm_d); cudaFree(dc.d_jacobian);
+    dc.d_ph2pr_f = dc.d_mm_f = nullptr; dc.d_ph2pr_d = dc.d_mm_d = nullptr; dc.d_jacobian = nullptr;
 }
 
 int phmm_create(const phmm_options* opt, phmm_engine** out)
@@ -1362,6 +1591,9 @@ int phmm_create(const phmm_options* opt, phmm_engine** out)
     int n_dev = std::max(1, e->opt.n_devices);
     int depth = e->opt.pipeline_depth > 0 ? e->opt.pipeline_depth : 2;
     e->host_threads = std::max(1, e->opt.host_threads);
+    // The device takes the final log10 only when the restated glibc algorithm IS this host's libm (self-test);
+    // PHMM_HOST_LOG10=1 forces the host pass (A/B measurements, paranoia).
+    e->device_log10 = log10_restatement_matches_libm() && getenv("PHMM_HOST_LOG10") == nullptr;
     static const bool trace_init = getenv("PHMM_TRACE_INIT") != nullptr;
     const auto ti0 = std::chrono::steady_clock::now();
     auto since = [&](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
@@ -1381,6 +1613,7 @@ int phmm_create(const phmm_options* opt, phmm_engine** out)
         //  tables and pools, which lets the sharding / gather path be exercised on a one-GPU box)
         dc->pool.reset(new HostPool(e->host_threads - 1));
         dc->fp64_first_opt = e->opt.fp64_first;
+        dc->device_log10 = e->device_log10;
         const auto tid = std::chrono::steady_clock::now();
         int rc = init_device(*dc, depth, err);
         if (trace_init) fprintf(stderr, "phmm init trace: device %d context + tables + %d slots %.1f ms\n", dc->ordinal, depth, since(tid));
@@ -1426,14 +1659,47 @@ static void drain_parts(phmm_engine* e, const std::vector<std::pair<int, int>>& 
     for (const auto& pr : parts) e->devs[pr.first]->slots[pr.second].busy = false;
 }
 
-int phmm_submit(phmm_engine* e, const phmm_batch* b, phmm_ticket* t)
+static int validate_sites(const phmm_batch* b, const phmm_sites* S, std::string& err)
+{
+    if (!S || S->n_sites < 0) { err = "sites is NULL"; return PHMM_ERR_INVALID_ARG; }
+    if (S->n_sites == 0) return PHMM_OK;
+    if (!S->site_region || !S->site_n_alleles || !S->hap_allele) { err = "NULL site array"; return PHMM_ERR_INVALID_ARG; }
+    int64_t at = 0;
+    for (int k = 0; k < S->n_sites; k++) {
+        const int g = S->site_region[k], A = S->site_n_alleles[k];
+        if (g < 0 || g >= b->n_regions || (k && g < S->site_region[k - 1])) { err = "site_region must be non-decreasing region indices"; return PHMM_ERR_INVALID_ARG; }
+        if (A < 1 || A > PHMM_MAX_ALLELES) { err = "site_n_alleles must be 1.." + std::to_string(PHMM_MAX_ALLELES); return PHMM_ERR_INVALID_ARG; }
+        const int nh = b->region_hap_beg[g + 1] - b->region_hap_beg[g];
+        for (int h = 0; h < nh; h++)
+            if (S->hap_allele[at + h] >= A) { err = "hap_allele names an allele the site does not have"; return PHMM_ERR_INVALID_ARG; }
+        at += nh;
+    }
+    return PHMM_OK;
+}
+
+static int submit_impl(phmm_engine* e, const phmm_batch* b, const phmm_sites* sites, phmm_ticket* t)
 {
     if (!e || !t) return PHMM_ERR_INVALID_ARG;
     DeviceGuard guard;
     std::string err;
     int rc = validate_batch(b, err);
     if (rc) { e->set_error(err); return rc; }
+    std::vector<int64_t> site_hap_off, site_read_off, gl_off;      // prefix sums over the sites (live until the pack phase is over)
+    if (sites) {
+        if (!e->device_log10) { e->set_error("the host's libm is not the glibc this library restates: no device-side reduction"); return PHMM_ERR_UNSUPPORTED; }
+        rc = validate_sites(b, sites, err);
+        if (rc) { e->set_error(err); return rc; }
+        const int ns = sites->n_sites;
+        site_hap_off.assign(ns + 1, 0); site_read_off.assign(ns + 1, 0); gl_off.assign(ns + 1, 0);
+        for (int k = 0; k < ns; k++) {
+            const int g = sites->site_region[k], A = sites->site_n_alleles[k];
+            site_hap_off[k + 1] = site_hap_off[k] + (b->region_hap_beg[g + 1] - b->region_hap_beg[g]);
+            site_read_off[k + 1] = site_read_off[k] + (b->region_read_beg[g + 1] - b->region_read_beg[g]);
+            gl_off[k + 1] = gl_off[k] + A * (A + 1) / 2;
+        }
+    }
     TicketRec rec;
+    rec.gl = sites != nullptr;
     rec.t0 = std::chrono::steady_clock::now();
     rec.n_pairs = b->n_regions ? batch_pairs(b, 0, b->n_regions) : 0;
     const int nd = (int)e->devs.size();
@@ -1470,6 +1736,14 @@ int phmm_submit(phmm_engine* e, const phmm_batch* b, phmm_ticket* t)
         const int g0 = cut[d], g1 = cut[d + 1];
         const bool exact = e->opt.exact_fp32 != 0, use_double = e->opt.use_double != 0;
         s.async_rc = PHMM_OK; s.async_err.clear();
+        s.gl = Slot::GlCtx();
+        if (sites) {                                          // the part's sites: those of regions [g0, g1)
+            s.gl.on = true;
+            s.gl.s0 = (int)(std::lower_bound(sites->site_region, sites->site_region + sites->n_sites, g0) - sites->site_region);
+            s.gl.s1 = (int)(std::lower_bound(sites->site_region, sites->site_region + sites->n_sites, g1) - sites->site_region);
+            s.gl.sites = sites;
+            s.gl.site_hap_off = site_hap_off.data(); s.gl.site_read_off = site_read_off.data(); s.gl.gl_off = gl_off.data();
+        }
         Slot* sp = &s;
         DeviceCtx* dcp = &dc;
         int* rc_out = &rcs[d];
@@ -1506,6 +1780,76 @@ int phmm_submit(phmm_engine* e, const phmm_batch* b, phmm_ticket* t)
     return PHMM_OK;
 }
 
+int phmm_submit(phmm_engine* e, const phmm_batch* b, phmm_ticket* t) { return submit_impl(e, b, nullptr, t); }
+
+int phmm_submit_gl(phmm_engine* e, const phmm_batch* b, const phmm_sites* sites, phmm_ticket* t)
+{
+    if (!sites) { if (e) e->set_error("sites is NULL"); return PHMM_ERR_INVALID_ARG; }
+    return submit_impl(e, b, sites, t);
+}
+
+int phmm_jacobian_table(const double** table, int32_t* n)
+{
+    int k = 0;
+    const double* tab = jacobian_table(&k);
+    if (table) *table = tab;
+    if (n) *n = k;
+    return PHMM_OK;
+}
+
+int phmm_wait_gl(phmm_engine* e, phmm_ticket t, phmm_gl_result* r)
+{
+    if (!e || !r) return PHMM_ERR_INVALID_ARG;
+    DeviceGuard guard;
+    TicketRec rec;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        auto it = e->tickets.find(t);
+        if (it == e->tickets.end() || !it->second.gl) return PHMM_ERR_BAD_TICKET;
+        rec = std::move(it->second);
+        e->tickets.erase(it);
+    }
+    int64_t n_gl = 0;
+    for (auto& pr : rec.parts) n_gl += e->devs[pr.first]->slots[pr.second].gl.n_gl;
+    if (n_gl && !r->genotype_lik) {
+        drain_parts(e, rec.parts);
+        e->set_error("result->genotype_lik is NULL");
+        return PHMM_ERR_INVALID_ARG;
+    }
+    const int np = (int)rec.parts.size();
+    std::vector<int> rcs(np, PHMM_OK);
+    std::vector<std::string> errs(np);
+    Latch latch(np);
+    for (int k = 0; k < np; k++) {
+        DeviceCtx& dc = *e->devs[rec.parts[k].first];
+        dc.post([&, k] {
+            rcs[k] = finalize_part_gl(e, *e->devs[rec.parts[k].first], e->devs[rec.parts[k].first]->slots[rec.parts[k].second], r, errs[k]);
+            latch.done();
+        });
+    }
+    latch.wait();
+    phmm_stats st{};
+    st.n_pairs = rec.n_pairs;
+    int rc_all = PHMM_OK;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        for (int k = 0; k < np; k++) {
+            Slot& s = e->devs[rec.parts[k].first]->slots[rec.parts[k].second];
+            const Part& p = s.part;
+            st.n_cells += p.n_cells; st.n_rescued += p.rescue_count;
+            st.h2d_bytes += (int64_t)p.h2d_bytes; st.d2h_bytes += (int64_t)p.d2h_bytes;
+            st.kernel_launches += p.launches;
+            st.kernel_ms = std::max(st.kernel_ms, p.kernel_ms);
+            st.n_devices_used++;
+            s.busy = false;
+            if (rcs[k] && !rc_all) { rc_all = rcs[k]; e->last_error = errs[k]; }
+        }
+    }
+    st.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - rec.t0).count();
+    r->stats = st;
+    return rc_all;
+}
+
 int phmm_wait(phmm_engine* e, phmm_ticket t, phmm_result* r)
 {
     if (!e || !r) return PHMM_ERR_INVALID_ARG;
@@ -1514,7 +1858,7 @@ int phmm_wait(phmm_engine* e, phmm_ticket t, phmm_result* r)
     {
         std::lock_guard<std::mutex> lk(e->mu);
         auto it = e->tickets.find(t);
-        if (it == e->tickets.end()) return PHMM_ERR_BAD_TICKET;
+        if (it == e->tickets.end() || it->second.gl) return PHMM_ERR_BAD_TICKET;
         rec = std::move(it->second);
         e->tickets.erase(it);
     }
@@ -1705,7 +2049,8 @@ int phmm_fetch_staged(phmm_engine* e, phmm_staged* st, phmm_result* r)
     dc.post([&] {
         Slot& s = st->slot;
         auto go = [&]() -> int {
-            const size_t out_bytes = 16 + sizeof(float) * (size_t)s.part.n_pairs;
+            const size_t n_pad = ((size_t)s.part.n_pairs + 3) / 4 * 4;
+            const size_t out_bytes = s.device_log10 ? 16 + sizeof(float) * (size_t)s.part.n_pairs : 16 + 2 * sizeof(float) * n_pad;
             CUDA_TRY(cudaMemcpyAsync(s.h_out.p, s.d_out.p, out_bytes, cudaMemcpyDeviceToHost, s.stream));
             CUDA_TRY(cudaEventRecord(s.ev_done, s.stream));
             s.part.d2h_bytes = out_bytes;

@@ -29,6 +29,28 @@ constexpr int kLongWarpsPerCta = 2;
 struct LongPair { int32_t read, hap; int64_t out_idx; };   // read / haplotype: indices into the part's offset arrays
 void launch_long_reads(const KernelArgs& args, const LongPair* pairs, int n_pairs, bool general, bool exact, bool use_double, cudaStream_t st);
 
+// phmm_finalize.cu: raw FP32 sums -> final float log10 values + counters, on the device (glibc's log10f restated)
+void launch_finalize(const float* raw32, int64_t n_pairs, float log10_init_f, float* lik32, unsigned* header, int sm_count,
+                     cudaStream_t st);
+
+// phmm_genotype.cu: cap / filter + per-site genotype likelihoods on the device; device pointers
+struct GenotypeArgs {
+    double* lik64;                       // [n_pairs] the capped double matrix (scratch; downloadable)
+    int64_t n_pairs;
+    int32_t n_regions, n_reads, n_sites;
+    const int32_t* region_read_beg; const int32_t* region_hap_beg; const int64_t* region_out_beg; const int32_t* read_off;
+    uint8_t* read_keep;                  // [n_reads] out: 0 = poorly modelled (intel_pairhmm.hpp:35-38)
+    const int32_t* site_region; const int32_t* site_n_alleles;
+    const int64_t* site_hap_off; const uint8_t* hap_allele;          // haplotype -> allele, per site
+    const int64_t* site_read_off; const uint8_t* read_overlap;       // read overlaps the site, per site (nullptr: all do)
+    const int64_t* gl_off;
+    double* scratch_al; uint8_t* scratch_used;                        // [site_read_off[n_sites]] x 8 doubles / bytes
+    double* gl; int32_t* site_n_used;    // out
+    const double* jacobian; double inv_step, log10_2;
+};
+void launch_genotype(const GenotypeArgs& g, const float* lik32, const RescueOut* rescue, const unsigned* rescue_count,
+                     double log10_init_d, int sm_count, cudaStream_t st);
+
 constexpr int kNumModes = 3;
 // tab[mode][aligned][shape][list]; aligned = every read length of the job is a multiple of K (constant-gap
 // modes only; the general mode has no aligned variant and its [1] row repeats [0]); list = the launch pulls its

@@ -14,8 +14,11 @@
 //                first 128*129/2 = 8256 entries are kept.
 // Must be compiled without FMA contraction and without fast-math (see Makefile).
 #include "phmm_tables.h"
+#include "phmm_log10.h"
 
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -80,6 +83,34 @@ const Tables& host_tables()
         g_tables = t;
     });
     return *g_tables;
+}
+
+bool log10_restatement_matches_libm()
+{
+    static const bool ok = [] {
+        uint32_t st = 0x2545f491u;
+        for (int i = 0; i < 100000; i++) {                  // floats: every exponent, random mantissas (x >= 0)
+            st ^= st << 13; st ^= st >> 17; st ^= st << 5;
+            const float x = l10_float(st % 0x7f800000u);
+            const float a = ::log10f(x), b = glibc_log10f(x);
+            if (l10_bits(a) != l10_bits(b)) {
+                if (getenv("PHMM_TRACE_INIT")) fprintf(stderr, "phmm init trace: log10f(%a) libm %a restated %a\n", x, a, b);
+                return false;
+            }
+        }
+        uint64_t s64 = 0x9e3779b97f4a7c15ull;
+        for (int i = 0; i < 50000; i++) {                   // doubles
+            s64 ^= s64 << 13; s64 ^= s64 >> 7; s64 ^= s64 << 17;
+            const double x = l10_double(s64 % 0x7ff0000000000000ull);
+            const double a = ::log10(x), b = glibc_log10(x);
+            if (l10_bits64(a) != l10_bits64(b)) {
+                if (getenv("PHMM_TRACE_INIT")) fprintf(stderr, "phmm init trace: log10(%a) libm %a restated %a\n", x, a, b);
+                return false;
+            }
+        }
+        return true;
+    }();
+    return ok;
 }
 
 }  // namespace phmm

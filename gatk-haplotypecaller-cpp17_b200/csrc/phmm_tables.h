@@ -15,4 +15,13 @@ struct Tables {
 
 const Tables& host_tables();
 
+// hc::MathUtils' Jacobian-logarithm table (utils/math_utils.hpp:17-29), 80 001 correctly rounded doubles
+// (phmm_jacobian.cpp).  inv_step = 1.0 / 0.0001, max tolerance 8.0.
+const double* jacobian_table(int* n);
+
+// True when the restatement of glibc's log10f / log10 (phmm_log10.h) agrees bit for bit with the libm this
+// process runs on, over a few hundred thousand sampled inputs: only then may the device take the final log10
+// (a host without FMA selects another variant of logf).  Evaluated once.
+bool log10_restatement_matches_libm();
+
 }  // namespace phmm

@@ -162,6 +162,45 @@ const char* phmm_strerror(int code);
 const char* phmm_last_error(const phmm_engine* e);
 int  phmm_abi_version(void);
 
+/*
+ * Device-side consumer of the matrix: per variant site, the diploid genotype likelihoods
+ * hc::Genetyper computes from the capped / filtered matrix (genotyper/genotyper.hpp:245-328: marginal_likelihoods,
+ * calculate_genotype_likelihoods, with utils/math_utils.hpp:11-30) -- bit for bit, so that the reads x haplotypes
+ * matrix never has to leave the GPU: the download shrinks to A (A + 1) / 2 doubles per site.  The host keeps what
+ * does not depend on the likelihoods (events, alleles, haplotype -> allele maps: genotyper.hpp:111-233, handed in
+ * as phmm_sites) and what consumes the vector (genotype quality and the call, :329-368).
+ *   site s belongs to region site_region[s] (non-decreasing) and has site_n_alleles[s] alleles (allele 0 = REF);
+ *   hap_allele: for every site in order, one byte per haplotype OF ITS REGION = the allele that haplotype carries
+ *               (Genetyper::get_haplotype_mapper, genotyper.hpp:224-232);
+ *   read_overlap: for every site in order, one byte per read OF ITS REGION, 1 = the read overlaps the site's
+ *               interval (get_read_indices_to_keep, :235-244), or NULL when every read does.
+ * Output: genotype_lik holds for every site in order its A (A + 1) / 2 likelihoods in the reference's genotype
+ * order ((a1, a2), a1 <= a2, a1 outer: genotyper.hpp:22-33).  Reads the poorly-modelled filter drops
+ * (intel_pairhmm.hpp:35-38) do not enter the sums, exactly as the reference erases them before genotyping.
+ * Needs a host whose libm is the glibc this library restates (phmm_log10.h; checked at phmm_create), otherwise
+ * PHMM_ERR_UNSUPPORTED: the host path (phmm_wait + the reference's own Genetyper) always works.
+ */
+#define PHMM_MAX_ALLELES 7      /* Genetyper::MAX_ALLELE_COUNT, genotyper.hpp:19 */
+typedef struct phmm_sites {
+    int32_t n_sites;
+    const int32_t* site_region;       /* [n_sites]                                       */
+    const int32_t* site_n_alleles;    /* [n_sites], 1..PHMM_MAX_ALLELES                  */
+    const uint8_t* hap_allele;        /* [sum_s n_haps(site_region[s])]                  */
+    const uint8_t* read_overlap;      /* [sum_s n_reads(site_region[s])] or NULL         */
+} phmm_sites;
+typedef struct phmm_gl_result {
+    double*  genotype_lik;            /* [sum_s A_s (A_s + 1) / 2] required                            */
+    int32_t* site_n_reads;            /* [n_sites] optional: reads that entered the sums               */
+    uint8_t* read_keep;               /* [n_reads] optional: 0 = poorly modelled read (erased)         */
+    double*  capped_lik;              /* [n_pairs] optional: the capped double matrix, row-major per region
+                                         (what compute_likelihoods returns before rows are erased)     */
+    phmm_stats stats;                 /* out */
+} phmm_gl_result;
+int  phmm_submit_gl(phmm_engine* e, const phmm_batch* b, const phmm_sites* sites, phmm_ticket* t);
+int  phmm_wait_gl(phmm_engine* e, phmm_ticket t, phmm_gl_result* r);
+/* The Jacobian-logarithm table the reduction indexes (utils/math_utils.hpp:17-29), for tests. */
+int  phmm_jacobian_table(const double** table, int32_t* n);
+
 /* Host-side cap + filter of one region's matrix, in place (intel_pairhmm.hpp:24-46).
  * keep[r] = 0 for reads to erase; returns the number kept.  Rows are not compacted. */
 int  phmm_normalize_filter(double* lik, int32_t n_reads, int32_t n_haps,

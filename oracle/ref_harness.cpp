@@ -27,6 +27,9 @@
 #include <cstring>
 
 #include "pairhmm/intel_pairhmm.hpp"   // pulls native/avx-pairhmm.h, sam.hpp, haplotype.hpp
+#define private public                 // Genetyper's marginalisation / genotype-likelihood helpers are private members
+#include "genotyper/genotyper.hpp"     // (the consumer of the matrix; pins oracle/genotype_oracle.c)
+#undef private
 #include "smithwaterman/intel_smithwaterman.hpp"   // the reference's SW aligner
 
 namespace {
@@ -173,6 +176,32 @@ int ref_sw_align(const uint8_t* ref, int nref, const uint8_t* alt, int nalt,
                                    std::string_view((const char*)alt, (size_t)nalt), prm);
     std::snprintf(cigar, (size_t)cap, "%s", cg.to_string().c_str());
     return (int)off;
+}
+
+
+// the reference's own marginal_likelihoods (genotyper.hpp:245-264) + calculate_genotype_likelihoods
+// (:311-327) for one site.  lik [n_reads][n_haps] is the matrix the genotyper receives (capped, erased rows already
+// gone); keep_idx are the indices get_read_indices_to_keep would return.  out: n_alleles (n_alleles + 1) / 2 doubles.
+int ref_genotype_likelihoods(const double* lik, int n_reads, int n_haps, const int32_t* keep_idx, int n_keep,
+                             int n_alleles, const uint8_t* hap_allele, double* out)
+{
+    hc::Genetyper g;
+    std::vector<std::vector<double>> m(n_reads, std::vector<double>(n_haps));
+    for (int r = 0; r < n_reads; r++) for (int h = 0; h < n_haps; h++) m[r][h] = lik[(size_t)r * n_haps + h];
+    std::vector<std::size_t> mapper(n_haps), idx(n_keep);
+    for (int h = 0; h < n_haps; h++) mapper[h] = hap_allele[h];
+    for (int k = 0; k < n_keep; k++) idx[k] = (std::size_t)keep_idx[k];
+    auto al = g.marginal_likelihoods((std::size_t)n_alleles, mapper, idx, m);
+    auto gl = g.calculate_genotype_likelihoods(al, (std::size_t)n_alleles);
+    for (std::size_t k = 0; k < gl.size(); k++) out[k] = gl[k];
+    return (int)gl.size();
+}
+
+// The reference's Jacobian table as compiled into ITS binary (math_utils.hpp:24-28, evaluated by GCC at compile time)
+const double* ref_jacobian_table(int* n)
+{
+    if (n) *n = (int)hc::MathUtils::JacobianLogTable::cache.size();
+    return hc::MathUtils::JacobianLogTable::cache.data();
 }
 
 } // extern "C"

@@ -84,6 +84,25 @@ class Checker:
         return {"log10": out, "raw32": raw32, "raw64": raw64, "rescued": resc}
 
 
+def _genotype(fn_oracle, fn_ref, lik, keep, use, n_alleles, hap_allele):
+    """Genotype likelihoods of one site from a capped region matrix [n_reads][n_haps]."""
+    lik = np.ascontiguousarray(lik, np.float64)
+    n_reads, n_haps = lik.shape
+    hap_allele = np.ascontiguousarray(hap_allele, np.uint8)
+    out = np.empty(n_alleles * (n_alleles + 1) // 2, np.float64)
+    keep = np.ones(n_reads, np.uint8) if keep is None else np.ascontiguousarray(keep, np.uint8)
+    use = np.ones(n_reads, np.uint8) if use is None else np.ascontiguousarray(use, np.uint8)
+    if fn_oracle is not None:
+        n = fn_oracle(lik, n_reads, n_haps, keep, use, n_alleles, hap_allele, out)
+    else:       # the reference takes the matrix the genotyper sees (erased rows gone) and the overlapping indices
+        rows = np.nonzero(keep)[0]
+        sub = np.ascontiguousarray(lik[rows])
+        idx = np.ascontiguousarray(np.nonzero(use[rows])[0], np.int32)
+        fn_ref(sub, len(rows), n_haps, idx, len(idx), n_alleles, hap_allele, out)
+        n = len(idx)
+    return out, int(n)
+
+
 def load_oracle():
     path = os.path.join(ORACLE_DIR, "liboracle.so")
     if not os.path.exists(path):
@@ -92,6 +111,12 @@ def load_oracle():
     ch = Checker(lib, "oracle")
     lib.oracle_normalize_filter.argtypes = [_f64p, C.c_int, C.c_int, _i32p, _u8p]
     lib.oracle_normalize_filter.restype = C.c_int
+    lib.oracle_genotype_likelihoods.argtypes = [_f64p, C.c_int, C.c_int, _u8p, _u8p, C.c_int, _u8p, _f64p]
+    lib.oracle_genotype_likelihoods.restype = C.c_int
+    lib.oracle_jacobian_table.argtypes = [C.POINTER(C.c_int)]
+    lib.oracle_jacobian_table.restype = C.POINTER(C.c_double)
+    ch.genotype_likelihoods = lambda lik, keep, use, n_alleles, hap_allele: _genotype(
+        lib.oracle_genotype_likelihoods, None, lik, keep, use, n_alleles, hap_allele)
     return ch
 
 
@@ -103,4 +128,9 @@ def load_ref():
     ch = Checker(lib, "ref")
     lib.ref_compute_likelihoods.argtypes = [C.c_int, _i32p, _u8p, _u8p, C.c_int, _i32p, _u8p, _f64p, _u8p]
     lib.ref_compute_likelihoods.restype = C.c_int
+    if hasattr(lib, "ref_genotype_likelihoods"):
+        lib.ref_genotype_likelihoods.argtypes = [_f64p, C.c_int, C.c_int, _i32p, C.c_int, C.c_int, _u8p, _f64p]
+        lib.ref_genotype_likelihoods.restype = C.c_int
+        ch.genotype_likelihoods = lambda lik, keep, use, n_alleles, hap_allele: _genotype(
+            None, lib.ref_genotype_likelihoods, lik, keep, use, n_alleles, hap_allele)
     return ch
