@@ -11,8 +11,10 @@
 //     with H(row-1), F and the haplotype bases of its columns in registers;
 //   * rows stream through the lanes as a wavefront (lane l works on row t - l at step t): the left
 //     neighbour's H and E of the row arrive by shuffle, the diagonal is the value received one step earlier;
-//   * back-track codes are one BYTE per cell, C contiguous bytes per lane and row, in a global scratch
-//     matrix with a pitch of 32 C (vector stores; nrow x pitch bytes, L2-resident);
+//   * back-track codes are FOUR BITS per cell (direction 0..2 | extension flags 4, 8: PairWiseSW.h:60-70), two
+//     cells per byte, C / 2 contiguous bytes per lane and row, in a global scratch matrix whose pitch is the
+//     alignment's own ceil(ncol / 2) rounded up to 16 bytes (a 415 x 415 pair: 86 KB; one byte per cell at a pitch
+//     of 32 C took 212 KB).  The host caps a launch by a scratch budget and walks larger batches in pieces;
 //   * the last row and last column of H go to shared memory; lane 0 replays the reference's anti-diagonal
 //     order over them to pick the end cell (PairWiseSW.h:329-357), walks the back-track matrix
 //     (getCIGAR, :367-520), merges equal neighbours and writes (op, length) pairs in CIGAR order.
@@ -21,6 +23,10 @@
 #include <cstdio>
 #include <cstring>
 #include <algorithm>
+#include <cstdlib>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 #include <cuda_runtime.h>
@@ -38,7 +44,7 @@ struct SwJob {
     int32_t ref_off, nrow, alt_off, ncol;
     int64_t bt_off;                                      // this alignment's back-track matrix in the scratch
     int32_t index;                                       // position in the caller's batch
-    int32_t pad;
+    int32_t pitch;                                       // bytes per back-track row: ceil(ncol / 2) rounded up to 16
 };
 
 struct SwArgs {
@@ -70,7 +76,7 @@ __global__ void __launch_bounds__(32) sw_kernel(const SwArgs a)
     const uint8_t* seq1 = a.ref_bases + job.ref_off;
     const uint8_t* seq2 = a.alt_bases + job.alt_off;
     uint8_t* bt = a.bt + job.bt_off;
-    constexpr int PITCH = 32 * C;
+    const int PITCH = job.pitch;
 
     for (int i = lane; i < nrow; i += 32) s_seq1[i] = seq1[i];
     const int j0 = lane * C;                             // columns j0+1 .. j0+C (1-based)
@@ -95,7 +101,7 @@ __global__ void __launch_bounds__(32) sw_kernel(const SwArgs a)
         if (i >= 1 && i <= nrow) {
             const uint8_t b1 = s_seq1[i - 1];
             int32_t hl = inH, e = inE, hd = dgL;
-            __align__(16) uint8_t row[C];
+            __align__(16) uint8_t row[C / 2];
 #pragma unroll
             for (int c = 0; c < C; c++) {
                 // MAIN_CODE (PairWiseSW.h:123-159)
@@ -112,18 +118,16 @@ __global__ void __launch_bounds__(32) sw_kernel(const SwArgs a)
                 if (f11 > h11) { b = kDelete; h11 = f11; }
                 hd = Hp[c];
                 Hp[c] = h11; F[c] = f11; e = e11; hl = h11;
-                row[c] = (uint8_t)(b | ext);
+                if (c & 1) row[c >> 1] |= (uint8_t)((b | ext) << 4);      // odd column: high nibble
+                else row[c >> 1] = (uint8_t)(b | ext);
             }
-            uint8_t* dst = bt + (size_t)(i - 1) * PITCH + j0;
-            if (C % 16 == 0) {
-#pragma unroll
-                for (int c = 0; c < C; c += 16) *reinterpret_cast<uint4*>(dst + c) = *reinterpret_cast<const uint4*>(row + c);
-            } else if (C % 8 == 0) {
-#pragma unroll
-                for (int c = 0; c < C; c += 8) *reinterpret_cast<uint2*>(dst + c) = *reinterpret_cast<const uint2*>(row + c);
-            } else {
-#pragma unroll
-                for (int c = 0; c < C; c += 4) *reinterpret_cast<uint32_t*>(dst + c) = *reinterpret_cast<const uint32_t*>(row + c);
+            // this lane's C / 2 bytes of the row; lanes wholly beyond the haplotype have nothing to keep
+            if (j0 < ncol) {
+                uint8_t* dst = bt + (size_t)(i - 1) * PITCH + (j0 >> 1);
+                if (C == 32) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(row);
+                else if (C == 16) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(row);
+                else if (C == 8) *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(row);
+                else *reinterpret_cast<uint16_t*>(dst) = *reinterpret_cast<const uint16_t*>(row);
             }
             dgL = inH;
             outH = hl; outE = e;
@@ -159,7 +163,7 @@ __global__ void __launch_bounds__(32) sw_kernel(const SwArgs a)
     if (j < ncol) push(kSoftclip, ncol - j);
     int state = 0;
     while (i > 0 && j > 0) {
-        const int btr = bt[(size_t)(i - 1) * PITCH + (j - 1)];
+        const int btr = (bt[(size_t)(i - 1) * PITCH + ((j - 1) >> 1)] >> (((j - 1) & 1) * 4)) & 15;
         if (state == kInsertExt) { j--; push(kInsert, 1); state = btr & kInsertExt; }
         else if (state == kDeleteExt) { i--; push(kDelete, 1); state = btr & kDeleteExt; }
         else switch (btr & 3) {
@@ -181,7 +185,7 @@ __global__ void __launch_bounds__(32) sw_kernel(const SwArgs a)
     }
 }
 
-struct Buf {
+struct DevBuf {
     void* p = nullptr; size_t cap = 0;
     cudaError_t reserve(size_t n) {
         if (n <= cap) return cudaSuccess;
@@ -192,7 +196,51 @@ struct Buf {
         if (e == cudaSuccess) cap = want;
         return e;
     }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
+struct HostBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        const size_t want = n + n / 4 + 4096;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// Everything the aligner owns on ONE device: a stream, two events, pinned staging and device buffers, all
+// grow-only and reused from call to call.  Keyed by the CUDA ordinal (a call for another device gets that device's
+// context, never this one's pointers), shared by all threads, calls on one device serialised by its mutex;
+// phmm_sw_release() frees the lot.
+struct SwCtx {
+    std::mutex mu;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    HostBuf h_in, h_out;
+    DevBuf d_in, d_out, d_bt;
+    void release() {
+        h_in.release(); h_out.release(); d_in.release(); d_out.release(); d_bt.release();
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        if (stream) cudaStreamDestroy(stream);
+        e0 = e1 = nullptr; stream = nullptr;
+    }
+};
+std::mutex g_sw_mu;
+std::map<int, std::unique_ptr<SwCtx>> g_sw_ctx;
+
+constexpr size_t kAlign = 256;
+inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
+// back-track scratch of one launch; larger batches are walked in pieces (PHMM_SW_SCRATCH_MB overrides)
+size_t scratch_budget()
+{
+    static const size_t b = [] { const char* v = getenv("PHMM_SW_SCRATCH_MB"); return (size_t)(v ? std::max(1, atoi(v)) : 1024) << 20; }();
+    return b;
+}
 
 #define SW_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { \
     std::fprintf(stderr, "phmm_sw_align: %s: %s\n", #expr, cudaGetErrorString(e__)); return PHMM_ERR_CUDA; } } while (0)
@@ -206,7 +254,24 @@ bool all_match(const uint8_t* ref, int nref, const uint8_t* alt, int nalt)
     return mismatch <= 2;
 }
 
+struct DeviceGuard {
+    int saved = -1;
+    DeviceGuard() { if (cudaGetDevice(&saved) != cudaSuccess) saved = -1; }
+    ~DeviceGuard() { if (saved >= 0) cudaSetDevice(saved); }
+};
+
 }  // namespace
+
+extern "C" void phmm_sw_release(void)
+{
+    std::lock_guard<std::mutex> lk(g_sw_mu);
+    DeviceGuard guard;
+    for (auto& kv : g_sw_ctx) {
+        std::lock_guard<std::mutex> lk2(kv.second->mu);
+        if (cudaSetDevice(kv.first) == cudaSuccess) kv.second->release();
+    }
+    g_sw_ctx.clear();
+}
 
 extern "C" int phmm_sw_align(int32_t device, const phmm_sw_batch* b, phmm_sw_result* r)
 {
@@ -217,14 +282,28 @@ extern "C" int phmm_sw_align(int32_t device, const phmm_sw_batch* b, phmm_sw_res
         return PHMM_ERR_INVALID_ARG;
     int visible = 0;
     if (cudaGetDeviceCount(&visible) != cudaSuccess || visible == 0 || device < 0 || device >= visible) return PHMM_ERR_NO_DEVICE;
+    DeviceGuard guard;                                   // the caller's current device is left as it was
     SW_TRY(cudaSetDevice(device));
+    SwCtx* ctx;
+    {
+        std::lock_guard<std::mutex> lk(g_sw_mu);
+        auto& slot = g_sw_ctx[device];
+        if (!slot) slot.reset(new SwCtx());
+        ctx = slot.get();
+    }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->stream) {
+        SW_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        SW_TRY(cudaEventCreate(&ctx->e0));
+        SW_TRY(cudaEventCreate(&ctx->e1));
+    }
+    cudaStream_t st = ctx->stream;
 
     // the aligner's all-match shortcut on the host; everything else grouped by columns-per-lane class
     const int n = b->n;
     std::vector<SwJob> jobs[4];                          // C = 4, 8, 16, 32
     std::vector<int32_t> n_elems(n, 0);
     std::vector<int32_t> match_len(n, 0);                // > 0: shortcut, the CIGAR is "<len>M"
-    int64_t bt_bytes = 0;
     for (int k = 0; k < n; k++) {
         const int nref = b->ref_off[k + 1] - b->ref_off[k], nalt = b->alt_off[k + 1] - b->alt_off[k];
         if (nref < 1 || nalt < 1) return PHMM_ERR_INVALID_ARG;                     // the reference throws (:33-34)
@@ -233,71 +312,89 @@ extern "C" int phmm_sw_align(int32_t device, const phmm_sw_batch* b, phmm_sw_res
         const uint8_t* alt = b->alt_bases + b->alt_off[k];
         if (all_match(ref, nref, alt, nalt)) { r->offset[k] = 0; n_elems[k] = 1; match_len[k] = nref; continue; }
         const int cls = nalt <= 128 ? 0 : nalt <= 256 ? 1 : nalt <= 512 ? 2 : 3;
-        SwJob j{b->ref_off[k], nref, b->alt_off[k], nalt, bt_bytes, k, 0};
-        bt_bytes += (int64_t)nref * 32 * (4 << cls);
-        jobs[cls].push_back(j);
+        const int pitch = (((nalt + 1) / 2) + 15) / 16 * 16;
+        jobs[cls].push_back(SwJob{b->ref_off[k], nref, b->alt_off[k], nalt, 0, k, pitch});
     }
-    const size_t n_jobs = jobs[0].size() + jobs[1].size() + jobs[2].size() + jobs[3].size();
+    std::vector<SwJob> all;
+    for (auto& v : jobs) all.insert(all.end(), v.begin(), v.end());
+    const size_t n_jobs = all.size();
     r->kernel_ms = 0.f;
-    std::vector<int32_t> h_off(n), h_ne(n);
-    std::vector<int64_t> h_start(n, 0);
-    std::vector<uint8_t> h_ops;
-    std::vector<int32_t> h_lens;
+    const uint8_t* h_ops = nullptr;
+    const int32_t* h_lens = nullptr;
+    const int64_t* h_start = nullptr;
     if (n_jobs) {
-        static thread_local Buf d_ref, d_alt, d_jobs, d_bt, d_off, d_ne, d_start, d_ops, d_lens, d_cursor;
+        // launches: consecutive jobs of one class whose back-track matrices fit the scratch budget
+        struct Piece { size_t first, count; int cls; size_t bt_bytes; };
+        std::vector<Piece> pieces;
+        size_t max_bt = 0;
+        {
+            size_t at = 0;
+            for (int cls = 0; cls < 4; cls++) {
+                const size_t end = at + jobs[cls].size();
+                while (at < end) {
+                    Piece pc{at, 0, cls, 0};
+                    while (at < end) {
+                        const size_t need = (size_t)all[at].nrow * all[at].pitch;
+                        if (pc.count && pc.bt_bytes + need > scratch_budget()) break;
+                        all[at].bt_off = (int64_t)pc.bt_bytes;
+                        pc.bt_bytes += need; pc.count++; at++;
+                    }
+                    max_bt = std::max(max_bt, pc.bt_bytes);
+                    pieces.push_back(pc);
+                }
+            }
+        }
+        // ONE pinned input block [ref bases | haplotype bases | jobs] and one upload
         const size_t ref_bytes = (size_t)b->ref_off[n], alt_bytes = (size_t)b->alt_off[n];
         const int64_t cap = r->cap_elems;
-        SW_TRY(d_ref.reserve(ref_bytes)); SW_TRY(d_alt.reserve(alt_bytes));
-        SW_TRY(d_jobs.reserve(sizeof(SwJob) * n_jobs)); SW_TRY(d_bt.reserve((size_t)bt_bytes));
-        SW_TRY(d_off.reserve(sizeof(int32_t) * n)); SW_TRY(d_ne.reserve(sizeof(int32_t) * n)); SW_TRY(d_start.reserve(sizeof(int64_t) * n));
-        SW_TRY(d_ops.reserve((size_t)cap)); SW_TRY(d_lens.reserve(sizeof(int32_t) * (size_t)cap)); SW_TRY(d_cursor.reserve(8));
-        std::vector<SwJob> all;
-        all.reserve(n_jobs);
-        for (auto& v : jobs) all.insert(all.end(), v.begin(), v.end());
-        SW_TRY(cudaMemcpy(d_ref.p, b->ref_bases, ref_bytes, cudaMemcpyHostToDevice));
-        SW_TRY(cudaMemcpy(d_alt.p, b->alt_bases, alt_bytes, cudaMemcpyHostToDevice));
-        SW_TRY(cudaMemcpy(d_jobs.p, all.data(), sizeof(SwJob) * n_jobs, cudaMemcpyHostToDevice));
-        SW_TRY(cudaMemset(d_cursor.p, 0, 8));
+        const size_t i_ref = 0, i_alt = align_up(ref_bytes), i_jobs = align_up(i_alt + alt_bytes), in_bytes = i_jobs + sizeof(SwJob) * n_jobs;
+        // outputs: [cursor | offset | n_elems | elem_start] come back first, then the used part of [ops | lens]
+        const size_t o_cursor = 0, o_off = 256, o_ne = align_up(o_off + sizeof(int32_t) * n), o_start = align_up(o_ne + sizeof(int32_t) * n),
+                     o_ops = align_up(o_start + sizeof(int64_t) * n), o_lens = align_up(o_ops + (size_t)cap), out_bytes = o_lens + sizeof(int32_t) * (size_t)cap;
+        SW_TRY(ctx->h_in.reserve(in_bytes)); SW_TRY(ctx->d_in.reserve(in_bytes));
+        SW_TRY(ctx->h_out.reserve(out_bytes)); SW_TRY(ctx->d_out.reserve(out_bytes));
+        SW_TRY(ctx->d_bt.reserve(max_bt));
+        uint8_t* hi = (uint8_t*)ctx->h_in.p;
+        std::memcpy(hi + i_ref, b->ref_bases, ref_bytes);
+        std::memcpy(hi + i_alt, b->alt_bases, alt_bytes);
+        std::memcpy(hi + i_jobs, all.data(), sizeof(SwJob) * n_jobs);
+        SW_TRY(cudaMemcpyAsync(ctx->d_in.p, hi, in_bytes, cudaMemcpyHostToDevice, st));
+        uint8_t* dout = (uint8_t*)ctx->d_out.p;
+        SW_TRY(cudaMemsetAsync(dout + o_cursor, 0, 8, st));
 
         SwArgs a{};
-        a.ref_bases = (const uint8_t*)d_ref.p; a.alt_bases = (const uint8_t*)d_alt.p;
+        a.ref_bases = (const uint8_t*)ctx->d_in.p + i_ref; a.alt_bases = (const uint8_t*)ctx->d_in.p + i_alt;
         a.w_match = b->w_match; a.w_mismatch = b->w_mismatch; a.w_open = b->w_open; a.w_extend = b->w_extend;
-        a.bt = (uint8_t*)d_bt.p; a.cap_elems = cap; a.cursor = (unsigned long long*)d_cursor.p;
-        a.offset = (int32_t*)d_off.p; a.n_elems = (int32_t*)d_ne.p; a.elem_start = (int64_t*)d_start.p;
-        a.ops = (uint8_t*)d_ops.p; a.lens = (int32_t*)d_lens.p;
-        cudaEvent_t e0, e1;
-        SW_TRY(cudaEventCreate(&e0)); SW_TRY(cudaEventCreate(&e1));
-        SW_TRY(cudaEventRecord(e0, 0));
-        size_t first = 0;
-        for (int cls = 0; cls < 4; cls++) {
-            const int nj = (int)jobs[cls].size();
-            if (!nj) continue;
-            a.jobs = (const SwJob*)d_jobs.p + first; a.n_jobs = nj;
-            switch (cls) {
-                case 0: sw_kernel<4><<<nj, 32>>>(a); break;
-                case 1: sw_kernel<8><<<nj, 32>>>(a); break;
-                case 2: sw_kernel<16><<<nj, 32>>>(a); break;
-                default: sw_kernel<32><<<nj, 32>>>(a); break;
+        a.bt = (uint8_t*)ctx->d_bt.p; a.cap_elems = cap; a.cursor = (unsigned long long*)(dout + o_cursor);
+        a.offset = (int32_t*)(dout + o_off); a.n_elems = (int32_t*)(dout + o_ne); a.elem_start = (int64_t*)(dout + o_start);
+        a.ops = dout + o_ops; a.lens = (int32_t*)(dout + o_lens);
+        SW_TRY(cudaEventRecord(ctx->e0, st));
+        for (const Piece& pc : pieces) {                 // pieces reuse the scratch: same stream, in order
+            a.jobs = (const SwJob*)((const uint8_t*)ctx->d_in.p + i_jobs) + pc.first; a.n_jobs = (int)pc.count;
+            switch (pc.cls) {
+                case 0: sw_kernel<4><<<(unsigned)pc.count, 32, 0, st>>>(a); break;
+                case 1: sw_kernel<8><<<(unsigned)pc.count, 32, 0, st>>>(a); break;
+                case 2: sw_kernel<16><<<(unsigned)pc.count, 32, 0, st>>>(a); break;
+                default: sw_kernel<32><<<(unsigned)pc.count, 32, 0, st>>>(a); break;
             }
             SW_TRY(cudaGetLastError());
-            first += nj;
         }
-        SW_TRY(cudaEventRecord(e1, 0));
-        SW_TRY(cudaEventSynchronize(e1));
-        SW_TRY(cudaEventElapsedTime(&r->kernel_ms, e0, e1));
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
-
-        unsigned long long used = 0;
-        SW_TRY(cudaMemcpy(&used, d_cursor.p, 8, cudaMemcpyDeviceToHost));
+        SW_TRY(cudaEventRecord(ctx->e1, st));
+        uint8_t* ho = (uint8_t*)ctx->h_out.p;
+        SW_TRY(cudaMemcpyAsync(ho, dout, o_ops, cudaMemcpyDeviceToHost, st));          // cursor + per-alignment scalars
+        SW_TRY(cudaStreamSynchronize(st));
+        SW_TRY(cudaEventElapsedTime(&r->kernel_ms, ctx->e0, ctx->e1));
+        const unsigned long long used = *(const unsigned long long*)(ho + o_cursor);
         if ((int64_t)used > cap) return PHMM_ERR_UNSUPPORTED;            // more CIGAR elements than cap_elems
-        h_ops.resize((size_t)used); h_lens.resize((size_t)used);
-        SW_TRY(cudaMemcpy(h_off.data(), d_off.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
-        SW_TRY(cudaMemcpy(h_ne.data(), d_ne.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
-        SW_TRY(cudaMemcpy(h_start.data(), d_start.p, sizeof(int64_t) * n, cudaMemcpyDeviceToHost));
         if (used) {
-            SW_TRY(cudaMemcpy(h_ops.data(), d_ops.p, (size_t)used, cudaMemcpyDeviceToHost));
-            SW_TRY(cudaMemcpy(h_lens.data(), d_lens.p, sizeof(int32_t) * (size_t)used, cudaMemcpyDeviceToHost));
+            SW_TRY(cudaMemcpyAsync(ho + o_ops, dout + o_ops, (size_t)used, cudaMemcpyDeviceToHost, st));
+            SW_TRY(cudaMemcpyAsync(ho + o_lens, dout + o_lens, sizeof(int32_t) * (size_t)used, cudaMemcpyDeviceToHost, st));
+            SW_TRY(cudaStreamSynchronize(st));
         }
+        const int32_t* h_off = (const int32_t*)(ho + o_off);
+        const int32_t* h_ne = (const int32_t*)(ho + o_ne);
+        h_start = (const int64_t*)(ho + o_start);
+        h_ops = ho + o_ops; h_lens = (const int32_t*)(ho + o_lens);
         for (const SwJob& j : all) { r->offset[j.index] = h_off[j.index]; n_elems[j.index] = h_ne[j.index]; }
     }
     // the caller's compact arrays, in batch order
@@ -308,8 +405,8 @@ extern "C" int phmm_sw_align(int32_t device, const phmm_sw_batch* b, phmm_sw_res
     for (int k = 0; k < n; k++) {
         const int64_t dst = r->elem_beg[k];
         if (match_len[k]) { r->ops[dst] = 'M'; r->lens[dst] = match_len[k]; continue; }
-        std::memcpy(r->ops + dst, h_ops.data() + h_start[k], (size_t)n_elems[k]);
-        std::memcpy(r->lens + dst, h_lens.data() + h_start[k], sizeof(int32_t) * (size_t)n_elems[k]);
+        std::memcpy(r->ops + dst, h_ops + h_start[k], (size_t)n_elems[k]);
+        std::memcpy(r->lens + dst, h_lens + h_start[k], sizeof(int32_t) * (size_t)n_elems[k]);
     }
     return PHMM_OK;
 }

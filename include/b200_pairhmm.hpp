@@ -263,18 +263,57 @@ struct B200PairHMM
 // that region -- capped rows, poorly modelled reads erased from the caller's vector
 // (intel_pairhmm.hpp:24-46) -- so the genotyper consumes it unchanged.  Regions may be taken in any
 // order, each once.  One thread calls add_region()/take() (the engine has one submitter).
+// One variant site of a region for the DEVICE-SIDE genotype reduction (phmm_submit_gl):
+// what Genetyper::assign_genotype_likelihoods knows about the site before it looks at a likelihood
+// (genotyper/genotyper.hpp:381-388): the allele count, the allele every haplotype carries (get_haplotype_mapper)
+// and which reads overlap the site's interval (get_read_indices_to_keep).  INTEGRATION.md shows where the
+// reference's loop is cut in two around it.
+struct B200Site
+{
+    int32_t n_alleles = 0;
+    std::vector<uint8_t> hap_allele;       // [haplotypes of the region]
+    std::vector<uint8_t> read_overlap;     // [reads of the region as handed to add_region], 1 = overlaps
+};
+
+// What the device hands back for a region submitted with sites: per site the diploid genotype likelihoods
+// (calculate_genotype_likelihoods, genotyper.hpp:322-327, bit for bit) in allele_index_cache order.
+struct B200RegionGL
+{
+    std::vector<std::vector<double>> site_genotype_likelihoods;
+    std::vector<int32_t> site_n_reads;     // reads that entered the sums
+    std::vector<uint8_t> read_keep;        // 0 = poorly modelled read (the reference erases it, intel_pairhmm.hpp:35-45)
+};
+
 class B200RegionBatcher
 {
 public:
-    explicit B200RegionBatcher(int64_t flush_cells = (int64_t)2e9, int32_t flush_regions = 4096, int max_in_flight = 3)
-        : flush_cells_(flush_cells), flush_regions_(flush_regions), max_in_flight_(max_in_flight), eng_(B200Engine::get()) {}
+    // device_gl: regions carry their variant sites (add_region(haps, reads, sites)) and come back as genotype
+    // likelihoods (take_gl) -- the reads x haplotypes matrix never leaves the GPU.
+    explicit B200RegionBatcher(int64_t flush_cells = (int64_t)2e9, int32_t flush_regions = 4096, int max_in_flight = 3,
+                               bool device_gl = false)
+        : flush_cells_(flush_cells), flush_regions_(flush_regions), max_in_flight_(max_in_flight), device_gl_(device_gl),
+          eng_(B200Engine::get()) {}
     ~B200RegionBatcher() { try { drain(); } catch (...) {} }
     B200RegionBatcher(const B200RegionBatcher&) = delete;
     B200RegionBatcher& operator=(const B200RegionBatcher&) = delete;
 
     template <class HaplotypeT, class ReadT>
+    int add_region(const std::vector<HaplotypeT>& haps, const std::vector<ReadT>& reads, const std::vector<B200Site>& sites)
+    {
+        if (!device_gl_) throw std::runtime_error("B200RegionBatcher: sites need a batcher constructed with device_gl = true");
+        for (const auto& st : sites)
+            if (st.hap_allele.size() != haps.size() || st.read_overlap.size() != reads.size() || st.n_alleles < 1 || st.n_alleles > PHMM_MAX_ALLELES)
+                throw std::runtime_error("B200RegionBatcher: site arrays do not match the region");
+        pending_sites_ = &sites;
+        const int id = add_region(haps, reads);
+        pending_sites_ = nullptr;
+        return id;
+    }
+
+    template <class HaplotypeT, class ReadT>
     int add_region(const std::vector<HaplotypeT>& haps, const std::vector<ReadT>& reads)
     {
+        if (device_gl_ && !pending_sites_) throw std::runtime_error("B200RegionBatcher: a device_gl batcher takes regions with their sites");
         if (!cur_) {
             cur_ = std::make_unique<Pending>();
             if (!free_slabs_.empty()) { cur_->slab = std::move(free_slabs_.back()); free_slabs_.pop_back(); }
@@ -282,6 +321,7 @@ public:
         }
         Pending& b = *cur_;
         Slabs& sl = *b.slab;
+        if (b.region_read_beg.empty()) { b.gl_off.assign(1, 0); b.region_site_beg.assign(1, 0); }
         if (b.region_read_beg.empty()) { b.region_read_beg.push_back(0); b.region_hap_beg.push_back(0); b.read_off.push_back(0); b.hap_off.push_back(0); b.out_beg.push_back(0); }
         int64_t read_bytes = 0, hap_bytes = 0;
         for (const auto& r : reads) {
@@ -300,6 +340,17 @@ public:
         b.region_hap_beg.push_back((int32_t)(b.hap_off.size() - 1));
         b.out_beg.push_back(b.out_beg.back() + (int64_t)reads.size() * (int64_t)haps.size());
         b.cells += read_bytes * hap_bytes;
+        if (device_gl_) {
+            const int32_t region = (int32_t)(b.region_read_beg.size() - 2);
+            for (const auto& st : *pending_sites_) {
+                b.site_region.push_back(region);
+                b.site_n_alleles.push_back(st.n_alleles);
+                b.hap_allele.insert(b.hap_allele.end(), st.hap_allele.begin(), st.hap_allele.end());
+                b.read_overlap.insert(b.read_overlap.end(), st.read_overlap.begin(), st.read_overlap.end());
+                b.gl_off.push_back(b.gl_off.back() + (int64_t)st.n_alleles * (st.n_alleles + 1) / 2);
+            }
+            b.region_site_beg.push_back((int32_t)b.site_region.size());
+        }
         const int id = (int)where_.size();
         where_.push_back({next_batch_id_, (int32_t)(b.region_read_beg.size() - 2)});
         if (b.cells >= flush_cells_ || (int32_t)(b.region_read_beg.size() - 1) >= flush_regions_) flush();
@@ -327,8 +378,18 @@ public:
         pb.gap_cont_c = (uint8_t)B200PairHMM::GAP_CONT;
         pb.hap_off = b.hap_off.data();
         pb.hap_bases = b.slab->hap_bases.data();
-        b.lik.resize((size_t)b.out_beg.back());
-        int rc = phmm_submit(eng_, &pb, &b.ticket);
+        int rc;
+        if (device_gl_) {
+            phmm_sites ps{};
+            ps.n_sites = (int32_t)b.site_region.size();
+            ps.site_region = b.site_region.data(); ps.site_n_alleles = b.site_n_alleles.data();
+            ps.hap_allele = b.hap_allele.data(); ps.read_overlap = b.read_overlap.data();
+            b.gl.resize((size_t)b.gl_off.back()); b.site_n_reads.resize(b.site_region.size()); b.read_keep.resize((size_t)pb.n_reads);
+            rc = phmm_submit_gl(eng_, &pb, &ps, &b.ticket);
+        } else {
+            b.lik.resize((size_t)b.out_beg.back());
+            rc = phmm_submit(eng_, &pb, &b.ticket);
+        }
         if (rc != PHMM_OK) throw std::runtime_error(std::string("phmm_submit: ") + phmm_strerror(rc) + ": " + phmm_last_error(eng_));
         b.submitted = true;
         ++in_flight_; ++batches_submitted;
@@ -367,6 +428,25 @@ public:
         return out;
     }
 
+    // The genotype likelihoods of a region added with its sites (device_gl batchers), each region once.
+    B200RegionGL take_gl(int region_id)
+    {
+        if (!device_gl_) throw std::runtime_error("B200RegionBatcher: take_gl needs device_gl = true");
+        if (region_id < 0 || region_id >= (int)where_.size()) throw std::runtime_error("B200RegionBatcher: unknown region id");
+        const Where w = where_[region_id];
+        if (w.batch == next_batch_id_) flush();
+        Pending& b = *batches_.at((size_t)(w.batch - first_batch_id_));
+        while (!b.done) wait_oldest();
+        B200RegionGL out;
+        const int32_t s0 = b.region_site_beg[w.region], s1 = b.region_site_beg[w.region + 1];
+        for (int32_t k = s0; k < s1; k++) {
+            out.site_genotype_likelihoods.emplace_back(b.gl.begin() + b.gl_off[k], b.gl.begin() + b.gl_off[k + 1]);
+            out.site_n_reads.push_back(b.site_n_reads[k]);
+        }
+        out.read_keep.assign(b.read_keep.begin() + b.region_read_beg[w.region], b.read_keep.begin() + b.region_read_beg[w.region + 1]);
+        return out;
+    }
+
     // wait for everything submitted so far
     void drain() { flush(); while (in_flight_) wait_oldest(); }
 
@@ -383,6 +463,11 @@ private:
         std::vector<int64_t> out_beg;
         std::unique_ptr<Slabs> slab;          // page-locked byte arrays; back to the free list once the batch is done
         std::vector<double> lik;
+        // device_gl: the sites of the batch and what comes back for them
+        std::vector<int32_t> site_region, site_n_alleles, region_site_beg, site_n_reads;
+        std::vector<uint8_t> hap_allele, read_overlap, read_keep;
+        std::vector<int64_t> gl_off;
+        std::vector<double> gl;
         int64_t cells = 0;
         phmm_ticket ticket = 0;
         bool submitted = false, done = false;
@@ -395,8 +480,16 @@ private:
             Pending& b = *pb;
             if (!b.submitted || b.done) continue;
             phmm_result res{};
-            res.log10_lik = b.lik.data();
-            int rc = phmm_wait(eng_, b.ticket, &res);
+            int rc;
+            if (device_gl_) {
+                phmm_gl_result gr{};
+                gr.genotype_lik = b.gl.data(); gr.site_n_reads = b.site_n_reads.data(); gr.read_keep = b.read_keep.data();
+                rc = phmm_wait_gl(eng_, b.ticket, &gr);
+                res.stats = gr.stats;
+            } else {
+                res.log10_lik = b.lik.data();
+                rc = phmm_wait(eng_, b.ticket, &res);
+            }
             if (rc != PHMM_OK) throw std::runtime_error(std::string("phmm_wait: ") + phmm_strerror(rc) + ": " + phmm_last_error(eng_));
             b.done = true; --in_flight_;
             b.slab->clear(); free_slabs_.push_back(std::move(b.slab));
@@ -412,6 +505,8 @@ private:
     int64_t flush_cells_;
     int32_t flush_regions_;
     int max_in_flight_;
+    bool device_gl_;
+    const std::vector<B200Site>* pending_sites_ = nullptr;
     phmm_engine* eng_;
     std::unique_ptr<Pending> cur_;
     std::vector<std::unique_ptr<Slabs>> free_slabs_;

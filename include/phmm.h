@@ -289,6 +289,9 @@ typedef struct phmm_sw_result {
     float    kernel_ms;               /* out: device time of the alignment kernels (CUDA events) */
 } phmm_sw_result;
 int  phmm_sw_align(int32_t device, const phmm_sw_batch* b, phmm_sw_result* r);
+/* The aligner keeps one context per device (stream, pinned staging, device buffers, grow-only, shared by all
+ * threads; calls on one device are serialised).  phmm_sw_release frees them all. */
+void phmm_sw_release(void);
 
 #ifdef __cplusplus
 }

@@ -56,13 +56,58 @@
 
 namespace {
 
+#ifdef HC_DEVICE_GL
+// Genetyper's constants (genotyper.hpp:16-19: declared before its first access label, i.e. private by class default,
+// out of reach of the `#define private public` above)
+constexpr std::size_t kAlleleExtension = 2, kMinHeterozygosityQuality = 50, kMaxAlleleCount = 7;
+// What Genetyper::assign_genotype_likelihoods (genotyper.hpp:369-397) knows about a site BEFORE it looks at a
+// likelihood -- its loop cut in two at the marginalize() call (:389).
+struct SitePlan {
+    std::vector<std::string> alleles;
+    hc::Interval alleles_loc;
+    std::size_t allele_count = 0;
+};
+#endif
+
 struct Window {
     hc::Interval origin, padded;
     std::vector<hc::SAMRecord> reads;
     std::vector<hc::Haplotype> haplotypes;
     std::string_view ref;
     int region_id = -1;
+#ifdef HC_DEVICE_GL
+    std::vector<SitePlan> plans;
+    std::vector<hc::B200Site> sites;
+#endif
 };
+
+#ifdef HC_DEVICE_GL
+// First half of assign_genotype_likelihoods: events, alleles, haplotype -> allele map, overlapping reads
+// (genotyper.hpp:376-389, every call the reference's own).
+void plan_sites(Window& w)
+{
+    hc::Genetyper g;
+    auto events_begins = g.set_events_for_haplotypes(w.haplotypes, w.ref, w.padded);
+    const auto& [contig, origin_begin, origin_end] = w.origin;
+    for (auto begin : events_begins) {
+        if (begin < origin_begin || begin >= origin_end) continue;
+        auto events = g.get_events_from_haplotypes(begin, w.haplotypes);
+        g.replace_span_dels(events, w.ref[begin - w.padded.begin], begin);
+        auto [alleles, alleles_loc] = g.get_compatible_alleles(events);
+        auto allele_count = alleles.size();
+        if (allele_count > kMaxAlleleCount) continue;
+        auto allele_mapper = g.get_allele_mapper(alleles, begin, w.haplotypes);
+        auto haplotype_mapper = g.get_haplotype_mapper(allele_mapper, w.haplotypes.size());
+        const auto overlap = alleles_loc.expand_within_contig(kAlleleExtension);
+        hc::B200Site site;
+        site.n_alleles = (int32_t)allele_count;
+        for (auto a : haplotype_mapper) site.hap_allele.push_back((uint8_t)a);
+        for (const auto& r : w.reads) site.read_overlap.push_back(r.get_interval().overlaps(overlap) ? 1 : 0);   // :235-244
+        w.sites.push_back(std::move(site));
+        w.plans.push_back({std::move(alleles), alleles_loc, allele_count});
+    }
+}
+#endif
 
 // hc::HaplotypeCaller::do_work (haplotypecaller.hpp:112-154) in passes; see the header comment.
 void do_work_batched(hc::HaplotypeCaller& caller, int n_threads, std::size_t region_size = 245, std::size_t padding_size = 85)
@@ -114,9 +159,15 @@ void do_work_batched(hc::HaplotypeCaller& caller, int n_threads, std::size_t reg
         for (auto& t : pool) t.join();
     }
     // pass 2: every region with more than one haplotype goes to the device, batched across windows
+#ifdef HC_DEVICE_GL
+    hc::B200RegionBatcher batcher((int64_t)2e9, 4096, 3, /*device_gl=*/true);
+    for (auto& w : windows)
+        if (!w.reads.empty() && w.haplotypes.size() > 1) { plan_sites(w); w.region_id = batcher.add_region(w.haplotypes, w.reads, w.sites); }
+#else
     hc::B200RegionBatcher batcher;
     for (auto& w : windows)
         if (!w.reads.empty() && w.haplotypes.size() > 1) w.region_id = batcher.add_region(w.haplotypes, w.reads);
+#endif
     batcher.flush();
     // pass 3 (window order): matrix, genotyper, VCF (:103-106)
     auto ofs = std::ofstream{caller.out_path};
@@ -127,9 +178,25 @@ void do_work_batched(hc::HaplotypeCaller& caller, int n_threads, std::size_t reg
     ofs << "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tNA12878\n";
     for (auto& w : windows) {
         if (w.region_id < 0) continue;
+#ifdef HC_DEVICE_GL
+        // second half of assign_genotype_likelihoods (genotyper.hpp:390-396) over the vectors the device computed
+        auto gl = batcher.take_gl(w.region_id);
+        hc::Genetyper genetyper;
+        std::vector<hc::Variant> variants;
+        for (std::size_t k = 0; k < w.plans.size(); k++) {
+            auto& plan = w.plans[k];
+            const auto& genotype_likelihoods = gl.site_genotype_likelihoods[k];
+            auto [genotype_index, genotype_quality] = genetyper.get_genotype_quality_and_max_genotype_index(genotype_likelihoods);
+            if (genotype_index == 0) continue;
+            auto genotype = genetyper.get_genotype(plan.allele_count, genotype_index);
+            if (genotype.first == 0 && genotype_quality < kMinHeterozygosityQuality) continue;
+            variants.emplace_back(std::move(plan.alleles_loc), std::move(plan.alleles), genotype, genotype_quality);
+        }
+#else
         auto likelihoods = batcher.take(w.region_id, w.reads);
         hc::Genetyper genetyper;
         auto variants = genetyper.assign_genotype_likelihoods(w.reads, w.haplotypes, likelihoods, w.ref, w.padded, w.origin);
+#endif
         for (const auto& variant : variants) variant.print(ofs);
     }
     std::fprintf(stderr, "hc_e2e: batched: %zu windows, %d batches, %lld pairs, %.3e cells, device kernels %.2f ms\n",
@@ -171,6 +238,8 @@ int main(int argc, char** argv)
         std::fprintf(stderr, "hc_e2e: engine=%s init_s=%.3f do_work_s=%.3f\n",
 #if defined(HC_USE_B200_SW)
                      "b200+sw",
+#elif defined(HC_DEVICE_GL)
+                     "b200-batched+device-gl",
 #elif defined(HC_BATCHED)
                      "b200-batched",
 #elif defined(HC_USE_B200)

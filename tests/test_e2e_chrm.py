@@ -17,6 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_EXE = os.path.join(ROOT, "oracle", "_ref", "hc_e2e_ref")
 B200_EXE = os.path.join(ROOT, "oracle", "_ref", "hc_e2e_b200")
 BATCHED_EXE = os.path.join(ROOT, "oracle", "_ref", "hc_e2e_b200_batched")
+GL_EXE = os.path.join(ROOT, "oracle", "_ref", "hc_e2e_b200_gl")
 GOLDEN = os.path.join(ROOT, "tests", "golden", "chrm_like.ref.vcf")
 needs = pytest.mark.skipif(not (os.path.exists(REF_EXE) and os.path.exists(B200_EXE)),
                            reason="oracle/_ref/hc_e2e_* not built (needs /root/reference at build time)")
@@ -70,4 +71,18 @@ def test_batched_driver_vcf_is_bit_identical(data, tmp_path, threads):
     out = str(tmp_path / "batched.vcf")
     t, log = _run(BATCHED_EXE, prefix, out, extra=("-T", str(threads)))
     print(f"\nchrM-like e2e wall, batched driver, {threads} assembly thread(s): {t:.2f} s ({log})")
+    assert open(out).read() == open(GOLDEN).read()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(GL_EXE), reason="oracle/_ref/hc_e2e_b200_gl not built")
+def test_device_genotype_reduction_vcf_is_bit_identical(data, tmp_path):
+    """SURVEY 8f-3 end to end: the reference's driver with Genetyper::assign_genotype_likelihoods cut in two around
+    the likelihoods -- sites planned on the host (the reference's own helpers), cap / filter / marginalisation /
+    genotype likelihoods computed ON THE DEVICE (phmm_submit_gl), genotype quality and the call on the host.
+    The reads x haplotypes matrix never comes back; the VCF is byte-identical to the reference's."""
+    prefix, _ = data
+    out = str(tmp_path / "gl.vcf")
+    t, log = _run(GL_EXE, prefix, out, extra=("-T", "8"))
+    print(f"\nchrM-like e2e wall, batched driver with device-side genotype likelihoods: {t:.2f} s ({log})")
     assert open(out).read() == open(GOLDEN).read()

@@ -419,3 +419,38 @@ def test_edge_cases_and_errors(pkg, engine, oracle):
     # the engine is still healthy afterwards
     b = B.from_regions([([b"ACGT"], [b"FFFF"], [b"ACGT"])])
     check(engine.compute(b), oracle.batch(b), what="after errors")
+
+
+def test_hunt_for_a_fast_vs_exact_rescue_flip(pkg, engine, exact_engine):
+    """The default engine contracts mul+add into FMA; its raw FP32 sum can differ from the reference's (= the exact
+    engine's, bit for bit) in the last place, so a pair whose raw sum lands within an ulp or two of MIN_ACCEPTED
+    (1e-28f, pairhmm_common.h:16) can take the other side of `raw < 1e-28f` (intel_pairhmm.hpp:137).  Hunt for such
+    pairs: ~1.5 million short reads whose likelihoods are spread densely around the threshold.  Whatever the count,
+    a flip may move the final log10 only by the FP32-vs-FP64 difference (<= 1e-4): the parity bar of north_star
+    holds, BIT identity of the VCF is guaranteed by exact_fp32 alone."""
+    rng = np.random.default_rng(2024)
+    alpha = np.frombuffer(b"ACGT", np.uint8)
+    n, R, H = 1_500_000, 24, 40
+    hap = alpha[rng.integers(0, 4, H)]
+    reads = np.tile(hap[8:8 + R], (n, 1))
+    # 8..12 mismatches on every other base (contiguous ones would be absorbed by one cheap insertion), random
+    # qualities: log10 L spreads over about [-70, -47] around the threshold at -64.1 = log10(1e-28 / 2^120)
+    n_mm = rng.integers(8, 13, n)
+    quals = (33 + rng.integers(20, 41, (n, R))).astype(np.uint8)
+    for k, i in enumerate(range(1, R, 2)):
+        hit = (k < n_mm)
+        reads[hit, i] = alpha[(np.searchsorted(alpha, reads[hit, i]) + 1) % 4]
+    b = pkg.Batch([0, n], [0, 1], np.arange(n + 1) * R, reads.reshape(-1), quals.reshape(-1), [0, H], hap)
+    fast, exact = engine.compute(b), exact_engine.compute(b)
+    thr = np.float32(1e-28)
+    ulps = np.abs(exact.raw32.view(np.int32).astype(np.int64) - thr.view(np.int32).astype(np.int64))
+    near = ulps <= 2
+    flips = fast.rescued != exact.rescued
+    frac_below = float((exact.raw32 < thr).mean())
+    print(f"\nrescue-flip hunt: {n} pairs, {frac_below:.1%} below 1e-28f, {int(near.sum())} within 2 ulp of it, "
+          f"{int(flips.sum())} fast-vs-exact rescue flips; raw FP32 differs in {int((fast.raw32 != exact.raw32).sum())} pairs")
+    assert 0.05 < frac_below < 0.95                                    # the hunt really straddles the threshold
+    assert (ulps[flips] <= 8).all()                                    # flips only ever happen AT the threshold
+    d = np.abs(fast.log10 - exact.log10)
+    assert np.nanmax(d) <= TOL32                                       # and never cost more than FP32-vs-FP64
+    assert np.array_equal(fast.rescued[~flips], exact.rescued[~flips])
