@@ -84,7 +84,7 @@ EXPORTS = ["phmm_create", "phmm_destroy", "phmm_compute", "phmm_submit", "phmm_w
            "phmm_last_error", "phmm_abi_version", "phmm_normalize_filter", "phmm_tables",
            "phmm_stage", "phmm_run_staged", "phmm_run_staged_ex", "phmm_run_staged_pipelined",
            "phmm_fetch_staged", "phmm_free_staged", "phmm_plan", "phmm_sw_align", "phmm_host_register",
-           "phmm_host_unregister", "phmm_host_alloc", "phmm_host_free", "phmm_submit_gl", "phmm_wait_gl", "phmm_jacobian_table", "phmm_sw_release"]
+           "phmm_host_unregister", "phmm_host_alloc", "phmm_host_free", "phmm_submit_gl", "phmm_wait_gl", "phmm_jacobian_table", "phmm_sw_release", "phmm_debug_check"]
 
 class _PlanInfo(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("mode", C.c_int32), ("n_jobs", C.c_int32), ("n_long_pairs", C.c_int32),
@@ -174,6 +174,7 @@ def lib():
         L.phmm_host_free.argtypes = [C.c_void_p]
         L.phmm_sw_align.argtypes = [C.c_int32, C.POINTER(_SwBatch), C.POINTER(_SwResult)]
         L.phmm_sw_release.argtypes = []; L.phmm_sw_release.restype = None
+        L.phmm_debug_check.argtypes = [C.c_void_p]; L.phmm_debug_check.restype = C.c_int64
         L.phmm_fetch_staged.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_Result)]
         L.phmm_free_staged.argtypes = [C.c_void_p, C.c_void_p]; L.phmm_free_staged.restype = None
         _lib = L
@@ -482,6 +483,10 @@ class PairHMMEngine:
 
     def __exit__(self, *a):
         self.close()
+
+    def debug_check(self):
+        """Guard bytes overwritten so far (PHMM_DEBUG_GUARD=1), see include/phmm.h."""
+        return int(self._L.phmm_debug_check(self._h))
 
     # -- phmm_compute / phmm_submit / phmm_wait
     def compute(self, batch, want_raw=True):

@@ -127,19 +127,48 @@ struct PinnedBuf {
     }
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
+// Debug aid standing in for compute-sanitizer (closed on this pool): with PHMM_DEBUG_GUARD=1 every device buffer is
+// allocated between two 4 KB guard zones filled with 0xA5 and its body is filled with the byte PHMM_POISON
+// (default 0xCD) -- also again on every reserve() that reuses the allocation.  phmm_debug_check() verifies the
+// guards (a write past either end of any buffer shows), and running a workload under two different poison bytes
+// must give bit-identical results (a read of memory no kernel wrote shows): tests/test_debug_guards.py.
+constexpr size_t kGuardBytes = 4096;
+inline bool debug_guard_on() { static const bool on = getenv("PHMM_DEBUG_GUARD") != nullptr; return on; }
+inline int debug_poison() { static const int v = [] { const char* s = getenv("PHMM_POISON"); return s ? (int)strtol(s, nullptr, 0) & 255 : 0xCD; }(); return v; }
+
 struct DeviceBuf {
     void* p = nullptr; size_t cap = 0;
+    void* base = nullptr;                // the allocation itself (== p unless guards are on)
     cudaError_t reserve(size_t n) {
-        if (n <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
+        if (n <= cap) {
+            if (debug_guard_on() && p) cudaMemset(p, debug_poison(), cap);          // stale contents must not matter either
+            return cudaSuccess;
+        }
+        release();
         size_t want = std::max(n, (size_t)1 << 20);
-        want = want + want / 4;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e == cudaSuccess) cap = want;
-        return e;
+        want = (want + want / 4 + 255) / 256 * 256;
+        const size_t g = debug_guard_on() ? kGuardBytes : 0;
+        cudaError_t e = cudaMalloc(&base, want + 2 * g);
+        if (e != cudaSuccess) { base = nullptr; return e; }
+        p = (uint8_t*)base + g; cap = want;
+        if (g) {
+            cudaMemset(base, 0xA5, g);
+            cudaMemset((uint8_t*)p + cap, 0xA5, g);
+            cudaMemset(p, debug_poison(), cap);
+        }
+        return cudaSuccess;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    // number of guard bytes that no longer hold 0xA5 (0 when guards are off)
+    int64_t check_guards() const {
+        if (!debug_guard_on() || !base) return 0;
+        std::vector<uint8_t> h(2 * kGuardBytes);
+        if (cudaMemcpy(h.data(), base, kGuardBytes, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        if (cudaMemcpy(h.data() + kGuardBytes, (const uint8_t*)p + cap, kGuardBytes, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        int64_t bad = 0;
+        for (uint8_t b : h) bad += (b != 0xA5);
+        return bad;
+    }
+    void release() { if (base) cudaFree(base); base = nullptr; p = nullptr; cap = 0; }
 };
 
 // ---- host-side parallel_for: planning, packing and the log10 pass of a batch are spread over the
@@ -1516,6 +1545,25 @@ int phmm_host_unregister(void* p)
 {
     if (!p) return PHMM_ERR_INVALID_ARG;
     return cudaHostUnregister(p) == cudaSuccess ? PHMM_OK : PHMM_ERR_CUDA;
+}
+
+int64_t phmm_debug_check(phmm_engine* e)
+{
+    // guard zones of every device buffer of every slot (PHMM_DEBUG_GUARD=1); call with nothing in flight
+    if (!e) return -1;
+    DeviceGuard guard;
+    int64_t bad = 0;
+    for (auto& dc : e->devs) {
+        cudaSetDevice(dc->ordinal);
+        cudaDeviceSynchronize();
+        for (auto& s : dc->slots)
+            for (const DeviceBuf* b : {&s.d_in, &s.d_jobs, &s.d_out, &s.d_rescue, &s.d_flags, &s.d_work, &s.d_sites, &s.d_gl_out, &s.d_lik64, &s.d_gl_scratch}) {
+                const int64_t k = b->check_guards();
+                if (k < 0) return -1;
+                bad += k;
+            }
+    }
+    return bad;
 }
 
 int phmm_host_alloc(size_t bytes, void** out)

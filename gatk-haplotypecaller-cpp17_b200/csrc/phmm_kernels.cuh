@@ -469,6 +469,13 @@ forward_kernel(const KernelArgs args)
                     for (int b = 0; b < 5; ++b)   // N on either side matches (:11,:21-26)
                         reinterpret_cast<S*>(reinterpret_cast<uint8_t*>(my_tab) + b * SUBT + k * 8)[hf] =
                             (rc == 4 || b == 4 || rc == b) ? mat : mis;
+                    // odd K: the last LDS.128 of a column also fetches entry K of the lane's sub-table row -- never used,
+                    // but it is a shared-memory read, so it reads a written value
+                    if ((K & 1) && k == K - 1) {
+#pragma unroll
+                        for (int b = 0; b < 5; ++b)
+                            reinterpret_cast<S*>(reinterpret_cast<uint8_t*>(my_tab) + b * SUBT + K * 8)[hf] = (S)0;
+                    }
                     if (!ALIGNED) P::set(pYY[k], hf, yy);
                     if (!CONSTG) {
                         P::set(pMM[k], hf, mm_);

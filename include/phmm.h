@@ -206,6 +206,12 @@ int  phmm_jacobian_table(const double** table, int32_t* n);
 int  phmm_normalize_filter(double* lik, int32_t n_reads, int32_t n_haps,
                            const int32_t* read_len, uint8_t* keep);
 
+/* Debug aid (compute-sanitizer is not available everywhere): with PHMM_DEBUG_GUARD=1 in the environment every
+ * device buffer of the engine sits between guard zones and starts out filled with the byte PHMM_POISON; this
+ * returns the number of guard bytes overwritten so far (0 = no out-of-bounds write; -1 = CUDA error; always 0
+ * without the variable).  Call with no ticket in flight.  See tests/test_debug_guards.py. */
+int64_t phmm_debug_check(phmm_engine* e);
+
 /* Read-only views of the host-built probability tables (native/Context.h:17-24), for tests. */
 int  phmm_tables(const float** ph2pr_f32, const float** mm_f32,
                  const double** ph2pr_f64, const double** mm_f64, int32_t* mm_entries);

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_exports_every_declared_symbol(pkg):
     hdr = open(os.path.join(ROOT, "include", "phmm.h")).read()
-    declared = set(re.findall(r"^\s*(?:const\s+char\*|int|void)\s+(phmm_\w+)\s*\(", hdr, re.M))
+    declared = set(re.findall(r"^\s*(?:const\s+char\*|int64_t|int|void)\s+(phmm_\w+)\s*\(", hdr, re.M))
     assert declared >= {"phmm_create", "phmm_destroy", "phmm_compute", "phmm_submit", "phmm_wait", "phmm_strerror"}
     L = pkg.lib()
     for name in sorted(declared):

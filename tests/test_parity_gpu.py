@@ -425,32 +425,52 @@ def test_hunt_for_a_fast_vs_exact_rescue_flip(pkg, engine, exact_engine):
     """The default engine contracts mul+add into FMA; its raw FP32 sum can differ from the reference's (= the exact
     engine's, bit for bit) in the last place, so a pair whose raw sum lands within an ulp or two of MIN_ACCEPTED
     (1e-28f, pairhmm_common.h:16) can take the other side of `raw < 1e-28f` (intel_pairhmm.hpp:137).  Hunt for such
-    pairs: ~1.5 million short reads whose likelihoods are spread densely around the threshold.  Whatever the count,
-    a flip may move the final log10 only by the FP32-vs-FP64 difference (<= 1e-4): the parity bar of north_star
-    holds, BIT identity of the VCF is guaranteed by exact_fp32 alone."""
+    pairs in two stages: (1) 1.5 million short reads whose likelihoods straddle the threshold by orders of magnitude;
+    (2) the read that came closest, with the qualities of its MATCHING bases redrawn 1.5 million times -- each of those
+    moves the likelihood by a few 1e-6 relative, which paves the last 1e-4 around the threshold at thousands of
+    pairs per float ulp.  Whatever the number of flips, a flip may move the final log10 only by the FP32-vs-FP64
+    difference (<= 1e-4): the parity bar of north_star holds; BIT identity of the VCF is what exact_fp32 is for
+    (INTEGRATION.md)."""
     rng = np.random.default_rng(2024)
     alpha = np.frombuffer(b"ACGT", np.uint8)
     n, R, H = 1_500_000, 24, 40
     hap = alpha[rng.integers(0, 4, H)]
-    reads = np.tile(hap[8:8 + R], (n, 1))
-    # 8..12 mismatches on every other base (contiguous ones would be absorbed by one cheap insertion), random
+    thr = np.float32(1e-28)
+
+    def run(reads, quals):
+        b = pkg.Batch([0, n], [0, 1], np.arange(n + 1) * R, reads.reshape(-1), quals.reshape(-1), [0, H], hap)
+        fast, exact = engine.compute(b), exact_engine.compute(b)
+        ulps = np.abs(exact.raw32.view(np.int32).astype(np.int64) - thr.view(np.int32).astype(np.int64))
+        flips = fast.rescued != exact.rescued
+        d = np.abs(fast.log10 - exact.log10)
+        assert np.nanmax(d) <= TOL32                                   # a flip never costs more than FP32-vs-FP64
+        assert (ulps[flips] <= 8).all()                                # and flips only ever happen AT the threshold
+        assert np.array_equal(fast.rescued[~flips], exact.rescued[~flips])
+        return fast, exact, ulps, flips
+
+    # stage 1: 8..12 mismatches on every other base (contiguous ones would be absorbed by one cheap insertion), random
     # qualities: log10 L spreads over about [-70, -47] around the threshold at -64.1 = log10(1e-28 / 2^120)
+    reads = np.tile(hap[8:8 + R], (n, 1))
     n_mm = rng.integers(8, 13, n)
     quals = (33 + rng.integers(20, 41, (n, R))).astype(np.uint8)
     for k, i in enumerate(range(1, R, 2)):
         hit = (k < n_mm)
         reads[hit, i] = alpha[(np.searchsorted(alpha, reads[hit, i]) + 1) % 4]
-    b = pkg.Batch([0, n], [0, 1], np.arange(n + 1) * R, reads.reshape(-1), quals.reshape(-1), [0, H], hap)
-    fast, exact = engine.compute(b), exact_engine.compute(b)
-    thr = np.float32(1e-28)
-    ulps = np.abs(exact.raw32.view(np.int32).astype(np.int64) - thr.view(np.int32).astype(np.int64))
-    near = ulps <= 2
-    flips = fast.rescued != exact.rescued
+    fast, exact, ulps, flips = run(reads, quals)
     frac_below = float((exact.raw32 < thr).mean())
-    print(f"\nrescue-flip hunt: {n} pairs, {frac_below:.1%} below 1e-28f, {int(near.sum())} within 2 ulp of it, "
-          f"{int(flips.sum())} fast-vs-exact rescue flips; raw FP32 differs in {int((fast.raw32 != exact.raw32).sum())} pairs")
     assert 0.05 < frac_below < 0.95                                    # the hunt really straddles the threshold
-    assert (ulps[flips] <= 8).all()                                    # flips only ever happen AT the threshold
-    d = np.abs(fast.log10 - exact.log10)
-    assert np.nanmax(d) <= TOL32                                       # and never cost more than FP32-vs-FP64
-    assert np.array_equal(fast.rescued[~flips], exact.rescued[~flips])
+    best = int(np.argmin(ulps))
+    print(f"\nrescue-flip hunt, stage 1: {n} pairs, {frac_below:.1%} below 1e-28f, closest {int(ulps[best])} ulp away, "
+          f"{int(flips.sum())} flips; raw FP32 differs in {int((fast.raw32 != exact.raw32).sum())} pairs")
+    # stage 2: that read, matching-base qualities redrawn (a match prior is 1 - 10^(-q/10): steps of ~1e-6 relative)
+    reads2 = np.tile(reads[best], (n, 1))
+    quals2 = np.tile(quals[best], (n, 1))
+    matching = np.array([i for i in range(R) if not (i % 2 == 1 and (i // 2) < n_mm[best])])
+    quals2[:, matching] = (33 + rng.integers(20, 41, (n, len(matching)))).astype(np.uint8)
+    quals2[0] = quals[best]
+    fast2, exact2, ulps2, flips2 = run(reads2, quals2)
+    near = ulps2 <= 2
+    print(f"rescue-flip hunt, stage 2: {n} variants of the closest read, {int(near.sum())} within 2 ulp of 1e-28f "
+          f"({int((ulps2 <= 8).sum())} within 8), {int(flips2.sum())} fast-vs-exact rescue flips, "
+          f"{int((fast2.raw32 != exact2.raw32).sum())} raw FP32 sums differ in the last place(s)")
+    assert (ulps2 <= 64).sum() > 100                                   # the second stage really paves the threshold

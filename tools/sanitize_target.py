@@ -1,4 +1,7 @@
-"""compute-sanitizer target (tools/sanitize.sh): one small pass over EVERY kernel family of libphmm_b200.so -- the
+"""Sanitizer target: runs under compute-sanitizer where that tool is available (tools/sanitize.sh) and, where it is
+not (it is closed on this pool: profiles/r02_sanitize_memcheck_refused.txt), under the library's own guard zones and
+poison fill (PHMM_DEBUG_GUARD=1, PHMM_POISON=<byte>; tests/test_debug_guards.py):  `--dump out.npz` stores every
+result so that runs under different poison bytes can be compared bit for bit.  One small pass over EVERY kernel family of libphmm_b200.so -- the
 ragged / lane-aligned / packed FP32 kernels in all three gap modes, the FP64 redo through its work list, the
 FP64-first order, the flush-exact tier, the long-read kernel, the device log10 + genotype reduction, the
 Smith-Waterman kernel -- with results checked against the oracle, so a sanitizer run is also a parity run."""
@@ -19,7 +22,11 @@ S = pkg.synth
 oracle = load_oracle()
 
 
+DUMP = {}
+
+
 def check(got, b, what):
+    DUMP[f"{len(DUMP):03d} {what}"] = np.concatenate([got.log10.view(np.uint8), got.raw32.view(np.uint8), got.raw64.view(np.uint8), got.rescued])
     want = oracle.batch(b, threads=8)
     resc = want["rescued"].astype(bool)
     assert np.array_equal(got.rescued.astype(bool), resc), what
@@ -73,9 +80,16 @@ with pkg.PairHMMEngine(devices=[0]) as eng, pkg.PairHMMEngine(devices=[0], exact
     per_site = [(g, 3, rng.integers(0, 3, int(b.haps_per_region[g])).astype(np.uint8), (rng.random(int(b.reads_per_region[g])) > 0.3).astype(np.uint8))
                 for g in range(b.n_regions) for _ in range(2)]
     gl = eng.compute_gl(b, pkg.Sites(b, per_site), want_matrix=True)
-    assert np.isfinite(gl.gl).all()
+    DUMP["gl"] = np.concatenate([gl.gl.view(np.uint8), gl.capped.view(np.uint8), gl.read_keep, gl.site_n_reads.view(np.uint8)])
+    guards = [e.debug_check() for e in (eng, ex, f64, two)]
+    print("guard bytes overwritten:", guards, flush=True)
+    assert guards == [0, 0, 0, 0]
+    assert not np.isnan(gl.gl).any()          # (-inf is legitimate: an allele no haplotype carries)
     print(f"ok  genotype reduction: {len(per_site)} sites", flush=True)
 pairs = sw_cases(5, 12)
 out, ms = pkg.sw_align(pairs)
+DUMP["sw"] = np.frombuffer(repr(out).encode(), np.uint8)
 print(f"ok  smith-waterman: {len(out)} alignments", flush=True)
+if "--dump" in sys.argv:
+    np.savez(sys.argv[sys.argv.index("--dump") + 1], **{k.replace("/", "_"): v for k, v in DUMP.items()})
 print("SANITIZE TARGET DONE")
