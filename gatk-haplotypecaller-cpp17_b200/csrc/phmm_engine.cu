@@ -141,7 +141,10 @@ struct DeviceBuf {
     void* base = nullptr;                // the allocation itself (== p unless guards are on)
     cudaError_t reserve(size_t n) {
         if (n <= cap) {
-            if (debug_guard_on() && p) cudaMemset(p, debug_poison(), cap);          // stale contents must not matter either
+            if (debug_guard_on() && p) {                     // stale contents must not matter either
+                cudaMemset(p, debug_poison(), cap);          // (null stream: the engine's streams do not wait for it,
+                cudaDeviceSynchronize();                     //  so wait here -- debug mode only)
+            }
             return cudaSuccess;
         }
         release();
@@ -155,6 +158,7 @@ struct DeviceBuf {
             cudaMemset(base, 0xA5, g);
             cudaMemset((uint8_t*)p + cap, 0xA5, g);
             cudaMemset(p, debug_poison(), cap);
+            cudaDeviceSynchronize();
         }
         return cudaSuccess;
     }
@@ -315,6 +319,7 @@ struct DeviceCtx {
     int next_slot = 0;
     float* d_ph2pr_f = nullptr; float* d_mm_f = nullptr;
     double* d_ph2pr_d = nullptr; double* d_mm_d = nullptr;
+    uint8_t* d_table_blob = nullptr;     // the one allocation the four probability tables live in
     double* d_jacobian = nullptr;        // hc::MathUtils' Jacobian table, uploaded by the first phmm_submit_gl part
     std::once_flag jacobian_once;
     // Two threads per device.  The WORKER plans, launches and finalizes (and serves the staged form); the
@@ -1412,25 +1417,44 @@ int init_slot(Slot& s, std::string& err)
 
 int init_device(DeviceCtx& dc, int depth, std::string& err)
 {
+    static const bool trace = getenv("PHMM_TRACE_INIT") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!trace) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "phmm init trace:   device %d %s %.1f ms\n", dc.ordinal, what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    };
     CUDA_TRY(cudaSetDevice(dc.ordinal));
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, dc.ordinal));
-    if (prop.major < 10) { err = "device is not sm_100 or newer"; return PHMM_ERR_NO_DEVICE; }
-    dc.sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaFree(nullptr));                              // the primary context is created here
+    lap("primary context");
+    int major = 0, sms = 0;                                   // (cudaGetDeviceProperties fills ~1 KB of mostly unused fields, slowly)
+    CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dc.ordinal));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dc.ordinal));
+    if (major < 10) { err = "device is not sm_100 or newer"; return PHMM_ERR_NO_DEVICE; }
+    dc.sm_count = sms;
+    lap("attributes");
     const Tables& T = host_tables();
-    CUDA_TRY(cudaMalloc(&dc.d_ph2pr_f, sizeof(float) * 128));
-    CUDA_TRY(cudaMalloc(&dc.d_mm_f, sizeof(float) * kMmEntries));
-    CUDA_TRY(cudaMalloc(&dc.d_ph2pr_d, sizeof(double) * 128));
-    CUDA_TRY(cudaMalloc(&dc.d_mm_d, sizeof(double) * kMmEntries));
-    CUDA_TRY(cudaMemcpy(dc.d_ph2pr_f, T.ph2pr_f.data(), sizeof(float) * 128, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(dc.d_mm_f, T.mm_f.data(), sizeof(float) * kMmEntries, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(dc.d_ph2pr_d, T.ph2pr_d.data(), sizeof(double) * 128, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(dc.d_mm_d, T.mm_d.data(), sizeof(double) * kMmEntries, cudaMemcpyHostToDevice));
+    lap("host tables");
+    // one allocation, one upload for the four probability tables
+    const size_t b_pf = sizeof(float) * 128, b_mf = sizeof(float) * kMmEntries, b_pd = sizeof(double) * 128, b_md = sizeof(double) * kMmEntries;
+    const size_t o_pd = 0, o_md = align_up(o_pd + b_pd), o_pf = align_up(o_md + b_md), o_mf = align_up(o_pf + b_pf), total = align_up(o_mf + b_mf);
+    std::vector<uint8_t> blob(total, 0);
+    std::memcpy(blob.data() + o_pd, T.ph2pr_d.data(), b_pd); std::memcpy(blob.data() + o_md, T.mm_d.data(), b_md);
+    std::memcpy(blob.data() + o_pf, T.ph2pr_f.data(), b_pf); std::memcpy(blob.data() + o_mf, T.mm_f.data(), b_mf);
+    uint8_t* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, total));
+    CUDA_TRY(cudaMemcpy(d, blob.data(), total, cudaMemcpyHostToDevice));
+    dc.d_table_blob = d;
+    dc.d_ph2pr_d = (double*)(d + o_pd); dc.d_mm_d = (double*)(d + o_md);
+    dc.d_ph2pr_f = (float*)(d + o_pf); dc.d_mm_f = (float*)(d + o_mf);
+    lap("device tables");
     dc.slots.resize(depth);
     for (auto& s : dc.slots) {
         int rc = init_slot(s, err);
         if (rc) return rc;
     }
+    lap("slots (streams, events)");
     return PHMM_OK;
 }
 
@@ -1625,8 +1649,8 @@ static void teardown_device(DeviceCtx& dc)
     cudaSetDevice(dc.ordinal);
     for (auto& s : dc.slots) { if (s.stream) cudaStreamSynchronize(s.stream); free_slot(s); }
     dc.slots.clear();
-    cudaFree(dc.d_ph2pr_f); cudaFree(dc.d_mm_f); cudaFree(dc.d_ph2pr_d); cudaFree(dc.d_mm_d); cudaFree(dc.d_jacobian);
-    dc.d_ph2pr_f = dc.d_mm_f = nullptr; dc.d_ph2pr_d = dc.d_mm_d = nullptr; dc.d_jacobian = nullptr;
+    cudaFree(dc.d_table_blob); cudaFree(dc.d_jacobian);
+    dc.d_table_blob = nullptr; dc.d_ph2pr_f = dc.d_mm_f = nullptr; dc.d_ph2pr_d = dc.d_mm_d = nullptr; dc.d_jacobian = nullptr;
 }
 
 int phmm_create(const phmm_options* opt, phmm_engine** out)

@@ -427,8 +427,8 @@ def test_hunt_for_a_fast_vs_exact_rescue_flip(pkg, engine, exact_engine):
     (1e-28f, pairhmm_common.h:16) can take the other side of `raw < 1e-28f` (intel_pairhmm.hpp:137).  Hunt for such
     pairs in two stages: (1) 1.5 million short reads whose likelihoods straddle the threshold by orders of magnitude;
     (2) the read that came closest, with the qualities of its MATCHING bases redrawn 1.5 million times -- each of those
-    moves the likelihood by a few 1e-6 relative, which paves the last 1e-4 around the threshold at thousands of
-    pairs per float ulp.  Whatever the number of flips, a flip may move the final log10 only by the FP32-vs-FP64
+    moves the likelihood by up to 1e-4 relative in steps far below a float ulp, which paves the neighbourhood of the
+    threshold at hundreds of pairs per ulp.  Whatever the number of flips, a flip may move the final log10 only by the FP32-vs-FP64
     difference (<= 1e-4): the parity bar of north_star holds; BIT identity of the VCF is what exact_fp32 is for
     (INTEGRATION.md)."""
     rng = np.random.default_rng(2024)
@@ -462,15 +462,24 @@ def test_hunt_for_a_fast_vs_exact_rescue_flip(pkg, engine, exact_engine):
     best = int(np.argmin(ulps))
     print(f"\nrescue-flip hunt, stage 1: {n} pairs, {frac_below:.1%} below 1e-28f, closest {int(ulps[best])} ulp away, "
           f"{int(flips.sum())} flips; raw FP32 differs in {int((fast.raw32 != exact.raw32).sum())} pairs")
-    # stage 2: that read, matching-base qualities redrawn (a match prior is 1 - 10^(-q/10): steps of ~1e-6 relative)
-    reads2 = np.tile(reads[best], (n, 1))
-    quals2 = np.tile(quals[best], (n, 1))
+    # stage 2: that read, about half of its matching-base qualities redrawn, the closest variant taken as the next
+    # centre, the quality band narrowed each round (a match prior is 1 - 10^(-q/10): ever finer steps)
+    n = 400_000
+    rd, q = reads[best].copy(), quals[best].copy()
     matching = np.array([i for i in range(R) if not (i % 2 == 1 and (i // 2) < n_mm[best])])
-    quals2[:, matching] = (33 + rng.integers(20, 41, (n, len(matching)))).astype(np.uint8)
-    quals2[0] = quals[best]
-    fast2, exact2, ulps2, flips2 = run(reads2, quals2)
-    near = ulps2 <= 2
-    print(f"rescue-flip hunt, stage 2: {n} variants of the closest read, {int(near.sum())} within 2 ulp of 1e-28f "
-          f"({int((ulps2 <= 8).sum())} within 8), {int(flips2.sum())} fast-vs-exact rescue flips, "
-          f"{int((fast2.raw32 != exact2.raw32).sum())} raw FP32 sums differ in the last place(s)")
-    assert (ulps2 <= 64).sum() > 100                                   # the second stage really paves the threshold
+    total_near = total_flips = 0
+    for band_lo in (20, 27, 32, 36):
+        reads2, quals2 = np.tile(rd, (n, 1)), np.tile(q, (n, 1))
+        redraw = rng.random((n, len(matching))) < 0.5
+        newq = (33 + rng.integers(band_lo, 41, (n, len(matching)))).astype(np.uint8)
+        quals2[:, matching] = np.where(redraw, newq, quals2[:, matching])
+        quals2[0] = q
+        fast2, exact2, ulps2, flips2 = run(reads2, quals2)
+        q = quals2[int(np.argmin(ulps2))].copy()
+        near = ulps2 <= 2
+        print(f"rescue-flip hunt, stage 2, quality band [{band_lo}, 40]: {n} variants, {int(near.sum())} within 2 ulp of 1e-28f "
+              f"({int((ulps2 <= 8).sum())} within 8), {int(flips2.sum())} fast-vs-exact rescue flips, "
+              f"{int((fast2.raw32 != exact2.raw32).sum())} raw FP32 sums differ in the last place(s)")
+        total_near += int(near.sum()); total_flips += int(flips2.sum())
+    print(f"rescue-flip hunt: {total_near} pairs within 2 ulp of the threshold examined, {total_flips} rescue decisions flipped by FMA contraction")
+    assert total_near >= 20                                            # the hunt really reached the threshold
