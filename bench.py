@@ -235,6 +235,62 @@ def helper_cpu_baseline(wl_key, budget_s=12.0):
                       "as_shipped_1_thread": round(g1, 3)}))
 
 
+def helper_sw_reference(n_pairs):
+    """--_helper sw_reference: the reference's own AVX2 aligner (hc::IntelSWAligner::align, one thread, as it runs
+    inside the assembler) on the first n_pairs of the bench's Smith-Waterman workload; prints GCUPS + the CIGARs' hash."""
+    import ctypes as C
+    import hashlib
+    from __graft_entry__ import load_package
+    pkg = load_package()
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_pairhmm.so")
+    if not os.path.exists(path):
+        print(json.dumps({"unavailable": "oracle/_ref not built"}))
+        return
+    lib = C.CDLL(path)
+    lib.ref_sw_align.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
+    pairs = pkg.synth.sw_pairs((int(n_pairs) + 15) // 16)[:int(n_pairs)]
+    buf = C.create_string_buffer(16384)
+    h = hashlib.sha256()
+    t0 = time.perf_counter()
+    for r, a in pairs:
+        off = lib.ref_sw_align(r, len(r), a, len(a), 200, -150, -260, -11, buf, 16384)
+        h.update(f"{off}:{buf.value.decode()};".encode())
+    dt = time.perf_counter() - t0
+    cells = sum(len(r) * len(a) for r, a in pairs)
+    print(json.dumps({"alignments": len(pairs), "gcups": round(cells / dt / 1e9, 3), "ms_per_alignment": round(1e3 * dt / len(pairs), 4),
+                      "threads": 1, "sha256": h.hexdigest(), "what": "hc::IntelSWAligner::align (AVX2), compiled from the reference"}))
+
+
+def sw_section(pkg, sms, sm_max_mhz):
+    """the batched Smith-Waterman kernel behind phmm_sw_align: 16 384 alignments (1 024 windows of 415 bases x
+    16 haplotypes), device time of the kernels and wall time of the whole call (strings in, CIGARs out)."""
+    import hashlib
+    pairs = pkg.synth.sw_pairs(1024)
+    cells = sum(len(r) * len(a) for r, a in pairs)
+    pkg.sw_align(pairs)
+    best_call, best_k, got = 1e9, 1e9, None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        got, kms = pkg.sw_align(pairs)
+        best_call, best_k = min(best_call, time.perf_counter() - t0), min(best_k, kms)
+    # the C ABI alone (arrays in, arrays out): what a C++ caller pays, without python's string handling
+    abi_s = pkg.sw_align_timed(pairs, repeats=3)
+    ref = run_helper("sw_reference", "512")
+    h = hashlib.sha256()
+    for off, cg in got[:512]:
+        h.update(f"{off}:{cg};".encode())
+    ALU_OPS_PER_CELL = 14                 # MAIN_CODE of PairWiseSW.h:123-159: 5 adds, 3 max, 6 compare / select for the back-track bits
+    peak = sms * 64 * sm_max_mhz * 1e6 / ALU_OPS_PER_CELL / 1e9
+    return {"workload": "16 384 alignments: 1 024 windows of 415 bases x 16 haplotypes (1-4 SNPs / indels each), NEW_SW_PARAMETERS",
+            "kernel_gcups": round(cells / best_k / 1e6, 1), "kernel_ms": round(best_k, 3),
+            "call_gcups_c_abi": round(cells / abi_s / 1e9, 1), "call_ms_c_abi": round(1e3 * abi_s, 3),
+            "call_over_kernel": round((best_k * 1e-3) / abi_s, 3),
+            "call_gcups_python_strings": round(cells / best_call / 1e9, 1),
+            "roofline": {"bound": "int32_alu", "peak": round(peak, 1), "frac": round(cells / best_k / 1e6 / peak, 3),
+                         "peak_def": f"{sms} SMs x 64 INT32 lanes x {sm_max_mhz:.0f} MHz / {ALU_OPS_PER_CELL} ALU ops per cell"},
+            "cpu_reference": ref, "identical_to_reference_on_sample": bool(ref.get("sha256") == h.hexdigest())}
+
+
 def helper_parity(npz_path):
     """--_helper parity: the oracle over the region slices saved by the GPU arm; prints the parity object."""
     from __graft_entry__ import load_package
@@ -522,6 +578,7 @@ def main():
     ap.add_argument("--exact", action="store_true", help="exact_fp32 engine (raw FP32 sums bit-identical to the reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-chrm", action="store_true")
+    ap.add_argument("--no-sw", action="store_true")
     ap.add_argument("--no-in-process", action="store_true")
     ap.add_argument("--_helper", nargs="+", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
@@ -530,6 +587,8 @@ def main():
             helper_cpu_baseline(args._helper[1])
         elif args._helper[0] == "parity":
             helper_parity(args._helper[1])
+        elif args._helper[0] == "sw_reference":
+            helper_sw_reference(args._helper[1])
         return
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -742,6 +801,11 @@ def main():
                 line["e2e_chrm"] = e2e_chrm_section(pkg)
             except Exception as ex:
                 line["e2e_chrm"] = {"unavailable": f"failed: {ex}"}
+        if world == 1 and not args.no_sw:
+            try:
+                line["sw"] = sw_section(pkg, sms, sm_max_mhz)
+            except Exception as ex:
+                line["sw"] = {"unavailable": f"failed: {ex}"}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = run_helper("cpu_baseline", args.workload)

@@ -137,6 +137,32 @@ def sw_align(pairs, params=SW_NEW_PARAMETERS, device=0, cap_elems=None):
     return out, float(r.kernel_ms)
 
 
+def sw_align_timed(pairs, params=SW_NEW_PARAMETERS, device=0, repeats=3):
+    """Best wall time in seconds of phmm_sw_align itself (arrays in, arrays out) over `repeats` calls: the cost of
+    the C ABI without this module's string packing / unpacking."""
+    import time
+    n = len(pairs)
+    refs = [np.frombuffer(bytes(r), np.uint8) for r, _ in pairs]
+    alts = [np.frombuffer(bytes(a), np.uint8) for _, a in pairs]
+    off = lambda xs: np.concatenate([[0], np.cumsum([len(x) for x in xs])]).astype(np.int32)
+    ref_off, alt_off = off(refs), off(alts)
+    ref_b, alt_b = np.ascontiguousarray(np.concatenate(refs)), np.ascontiguousarray(np.concatenate(alts))
+    cap = 32 * n + 4096
+    offset = np.zeros(n, np.int32); elem_beg = np.zeros(n + 1, np.int64)
+    ops = np.zeros(cap, np.uint8); lens = np.zeros(cap, np.int32)
+    b = _SwBatch(n, ref_off.ctypes.data, ref_b.ctypes.data, alt_off.ctypes.data, alt_b.ctypes.data, *params)
+    r = _SwResult(offset.ctypes.data, elem_beg.ctypes.data, cap, ops.ctypes.data, lens.ctypes.data, 0.0)
+    best = 1e9
+    for _ in range(repeats + 1):
+        t0 = time.perf_counter()
+        rc = lib().phmm_sw_align(device, C.byref(b), C.byref(r))
+        dt = time.perf_counter() - t0
+        if rc != PHMM_OK:
+            raise PhmmError(rc, lib().phmm_strerror(rc).decode())
+        best = min(best, dt)
+    return best
+
+
 _lib = None
 
 

@@ -315,6 +315,8 @@ struct DeviceCtx {
     int fp64_first_opt = 0;              // phmm_options.fp64_first
     bool device_log10 = false;           // phmm_engine::device_log10
     std::unique_ptr<HostPool> pool;      // host_threads - 1 helpers for this device's worker thread
+    std::unique_ptr<HostPool> pack_pool; // helpers of the PACKER thread (its copies must not queue behind the worker's
+                                         // planning and finalizing in the same pool: a HostPool runs one parallel_for at a time)
     std::vector<Slot> slots;
     int next_slot = 0;
     float* d_ph2pr_f = nullptr; float* d_mm_f = nullptr;
@@ -909,7 +911,7 @@ int stage_pack(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1, int6
     p = Part();
     p.g0 = g0; p.g1 = g1; p.out0 = out0;
     p.n_regions = g1 - g0;
-    HostPool& pool = *dc.pool;
+    HostPool& pool = *dc.pack_pool;
     {   // test hook (tests/test_multi_device_gpu.py): PHMM_FAULT_PACK=<first region> makes the pack phase of the
         // share that starts at that region fail ONCE, to exercise the partial-failure path of phmm_submit
         static std::atomic<int> fault_at{[] { const char* v = getenv("PHMM_FAULT_PACK"); return v ? atoi(v) : -1; }()};
@@ -1684,6 +1686,7 @@ int phmm_create(const phmm_options* opt, phmm_engine** out)
         // (an ordinal may be listed more than once: every entry is an independent worker with its own streams,
         //  tables and pools, which lets the sharding / gather path be exercised on a one-GPU box)
         dc->pool.reset(new HostPool(e->host_threads - 1));
+        dc->pack_pool.reset(new HostPool(std::max(0, e->host_threads / 2 - 1)));
         dc->fp64_first_opt = e->opt.fp64_first;
         dc->device_log10 = e->device_log10;
         const auto tid = std::chrono::steady_clock::now();

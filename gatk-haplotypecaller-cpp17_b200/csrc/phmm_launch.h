@@ -11,15 +11,18 @@ using KernelFn = void (*)(const KernelArgs);
 // bases in one pass (one dummy row on top is mandatory, see phmm_kernels.cuh).
 struct Shape { int G, K; };
 
-// Shapes compiled in this round.  Wide groups (G=32) keep registers low; narrow groups (G=16) put
-// more rows in a lane: fewer fill/drain steps and more FP32 work per shuffle/loop instruction.
-// The last three are the PACKED shapes (free-width lane groups on the whole warp, phmm_kernels.cuh): they
-// only exist as "aligned" kernels of the constant-gap modes and are never picked by read length alone.
-constexpr int kNumShapes = 21;
-constexpr int kFirstPackedShape = 18;
+// Shapes compiled.  Narrow groups (G = 16) put more rows in a lane -- fewer fill/drain steps, more FP32 work per
+// shuffle and loop instruction -- and win the planner's cost model G (15 K + 10) (H + G - 1) for every read they can
+// hold (R <= 159); the wide groups (G = 32) are only ever picked for reads of 160..255 bases, so only K = 6, 7, 8 of
+// them exist (the five smaller ones were a quarter of the fatbin and never launched: shape histogram over S2..S5 and
+// the chrM-like contig).  The last three are the PACKED shapes (free-width lane groups on the whole warp,
+// phmm_kernels.cuh): they only exist as "aligned" kernels of the constant-gap modes and are never picked by read
+// length alone.
+constexpr int kNumShapes = 16;
+constexpr int kFirstPackedShape = 13;
 constexpr Shape kShapes[kNumShapes] = {
-    {32, 1}, {32, 2}, {32, 3}, {32, 4}, {32, 5}, {32, 6}, {32, 7}, {32, 8},
     {16, 1}, {16, 2}, {16, 3}, {16, 4}, {16, 5}, {16, 6}, {16, 7}, {16, 8}, {16, 9}, {16, 10},
+    {32, 6}, {32, 7}, {32, 8},
     {32, 8}, {32, 9}, {32, 10}};
 constexpr int kMaxReadLenCompiled = 32 * 8 - 1;   // 255
 

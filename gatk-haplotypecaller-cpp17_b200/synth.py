@@ -185,6 +185,28 @@ def s5_batch(n_windows, seed=SEEDS["S5"], procs=None, chunk=256):
         return B.concat(pool.map(_s5_chunk, jobs))
 
 
+def sw_pairs(n_regions, n_haps=16, seed=11, window=415):
+    """Smith-Waterman workload: every haplotype of a padded window aligned to that window, as
+    assembler/graph_wrapper.hpp:232-239 does; haplotypes = the window with 1-4 SNPs / small indels each.
+    Returns [(window bytes, haplotype bytes)]."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n_regions):
+        ref = ACGT[rng.integers(0, 4, window)]
+        for _h in range(n_haps):
+            alt = list(ref)
+            for _e in range(int(rng.integers(1, 5))):
+                k = int(rng.integers(10, len(alt) - 10)); t = int(rng.integers(0, 3))
+                if t == 0:
+                    alt[k] = int(ACGT[rng.integers(0, 4)])
+                elif t == 1:
+                    del alt[k:k + int(rng.integers(1, 8))]
+                else:
+                    alt[k:k] = [int(x) for x in ACGT[rng.integers(0, 4, int(rng.integers(1, 8)))]]
+            out.append((ref.tobytes(), np.array(alt, np.uint8).tobytes()))
+    return out
+
+
 def random_small(seed, n_regions=3, max_reads=9, max_haps=5, max_read_len=70, max_hap_len=120,
                  general_gaps=True, n_frac=0.03, lower_frac=0.0):
     """Ragged little regions with N bases and arbitrary qualities: parity-test fodder."""
