@@ -418,7 +418,10 @@ def e2e_run(pkg, eng, batches, steps, warmup, barrier=None, clk=None):
     cap = max(b.n_pairs for b in batches)                         # batches of a ragged stream differ in size
     results = [pkg.Result(cap, want_raw=False) for _ in range(2)]
     nb = len(batches)
-    for w in range(max(warmup, DEPTH)):                           # also grows every slot's buffers
+    biggest = max(batches, key=lambda b: b.input_bytes + 8 * b.n_pairs)
+    for w in range(DEPTH):                                        # every slot of the ring grows its (grow-only) buffers to the
+        eng.compute(biggest, want_raw=False)                      # largest batch of the stream: no re-allocation while timed
+    for w in range(warmup):
         eng.compute(batches[w % nb], want_raw=False)
     if barrier:
         barrier()
@@ -653,7 +656,8 @@ def main():
     eng = pkg.PairHMMEngine(devices=[local], pipeline_depth=DEPTH, host_threads=4, exact_fp32=args.exact)
     # distinct batches per rank (weak scaling: every GPU gets its own `regions` regions per step)
     cells_per_step = float(np.mean([b.n_cells for b in batches]))
-    staged = [eng.stage(b) for b in batches]
+    eng.compute(batches[-1], want_raw=False)                       # as inside a stream: the planner's choices that follow the
+    staged = [eng.stage(b) for b in batches]                       # previous batch (FP64-first for rescue-dense input) are made
     in_bytes = int(np.mean([b.input_bytes for b in batches]))
     out_bytes = int(np.mean([4 * b.n_pairs for b in batches]))
     resident_mb = sum(b.input_bytes + 20 * b.n_pairs for b in batches) / 1e6
@@ -801,6 +805,13 @@ def main():
                 line["e2e_chrm"] = e2e_chrm_section(pkg)
             except Exception as ex:
                 line["e2e_chrm"] = {"unavailable": f"failed: {ex}"}
+        if world == 1 and not args.no_chrm and args.workload == "s3":
+            exe = os.path.join(ROOT, "tools", "cpp_surface_bench")
+            try:                                                   # the reference-facing C++ surface, from std::string reads
+                r = subprocess.run([exe, "1024", "64"], capture_output=True, text=True, timeout=300)
+                line["e2e_cpp_surface"] = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else {"unavailable": r.stderr[-300:]}
+            except Exception as ex:
+                line["e2e_cpp_surface"] = {"unavailable": f"{ex}"}
         if world == 1 and not args.no_sw:
             try:
                 line["sw"] = sw_section(pkg, sms, sm_max_mhz)

@@ -9,6 +9,7 @@ kind = sys.argv[2] if len(sys.argv) > 2 else "s3"
 b = {"s3": lambda: pkg.synth.s3(n), "s3g": lambda: pkg.synth.s3(n, general_gaps=True),
      "s2": lambda: pkg.synth.s2(n), "s4": lambda: pkg.synth.s4(n)}[kind]()
 with pkg.PairHMMEngine(devices=[0]) as eng:
+    eng.compute(b, want_raw=False)          # as in a stream: the order of the precision passes follows the previous batch
     st = eng.stage(b)
     eng.run_staged(st, 1)
     ms, nl = eng.run_staged(st, 3)

@@ -7,6 +7,7 @@ pkg = load_package()
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 b = next(pkg.synth.s5_stream(n, windows_per_batch=n))
 with pkg.PairHMMEngine(devices=[0]) as eng:
+    eng.compute(b, want_raw=False)
     st = eng.stage(b)
     eng.run_staged(st, 1)
     ms, nl = eng.run_staged(st, 1)

@@ -14,21 +14,21 @@ if has launches; then
   for spec in "64 s4" "128 s3g"; do
     set -- $spec
     python tools/prof_s3.py $1 $2 > ${O}_plain_$2_$1.log 2>&1 &&
-    ncu --metrics gpu__time_duration.sum --clock-control none -c 64 --csv --log-file ${O}_launches_$2_$1.csv python tools/prof_s3.py $1 $2 > /dev/null 2>&1
+    ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file ${O}_launches_$2_$1.csv python tools/prof_s3.py $1 $2 > /dev/null 2>&1
   done
   python tools/prof_s5.py 1024 > ${O}_plain_s5.log 2>&1 &&
-  ncu --metrics gpu__time_duration.sum --clock-control none -c 100 --csv --log-file ${O}_launches_s5.csv python tools/prof_s5.py 1024 > /dev/null 2>&1
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 160 --csv --log-file ${O}_launches_s5.csv python tools/prof_s5.py 1024 > /dev/null 2>&1
 fi
 full() {  # name, skip, count, cmd...
   local name=$1 skip=$2 cnt=$3; shift 3
-  ncu --set full --clock-control none --import-source on -s $skip -c $cnt -o /tmp/${TAG}_$name "$@" > ${O}_ncu_$name.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:forward_kernel -s $skip -c $cnt -o /tmp/${TAG}_$name "$@" > ${O}_ncu_$name.log 2>&1
   python tools/ncu_summary.py /tmp/${TAG}_$name.ncu-rep ${O}_ncu_$name.txt
   rm -f /tmp/${TAG}_$name.ncu-rep
 }
-if has ncu_s4; then full s4 8 4 python tools/prof_s3.py 64 s4; fi
-if has ncu_s3g; then full s3g 2 2 python tools/prof_s3.py 128 s3g; fi
-if has ncu_s3; then full s3 2 2 python tools/prof_s3.py 128 s3; fi
-if has ncu_s5; then full s5 24 12 python tools/prof_s5.py 1024; fi
+if has ncu_s4; then full s4 20 6 python tools/prof_s3.py 64 s4; fi
+if has ncu_s3g; then full s3g 4 2 python tools/prof_s3.py 128 s3g; fi
+if has ncu_s3; then full s3 4 2 python tools/prof_s3.py 128 s3; fi
+if has ncu_s5; then full s5 48 4 python tools/prof_s5.py 1024; fi
 du -sh gpurun_out; ls -la gpurun_out
 if has mode0exp; then
   for g in 16 32; do PHMM_FORCE_GROUP=$g python tools/prof_s3.py 128 s3g > ${O}_mode0_forceG$g.log 2>&1; done
