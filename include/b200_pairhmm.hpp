@@ -289,7 +289,7 @@ class B200RegionBatcher
 public:
     // device_gl: regions carry their variant sites (add_region(haps, reads, sites)) and come back as genotype
     // likelihoods (take_gl) -- the reads x haplotypes matrix never leaves the GPU.
-    explicit B200RegionBatcher(int64_t flush_cells = (int64_t)2e9, int32_t flush_regions = 4096, int max_in_flight = 3,
+    explicit B200RegionBatcher(int64_t flush_cells = (int64_t)1.6e10, int32_t flush_regions = 4096, int max_in_flight = 3,
                                bool device_gl = false)
         : flush_cells_(flush_cells), flush_regions_(flush_regions), max_in_flight_(max_in_flight), device_gl_(device_gl),
           eng_(B200Engine::get()) {}
@@ -409,21 +409,21 @@ public:
         const int32_t h0 = b.region_hap_beg[w.region], h1 = b.region_hap_beg[w.region + 1];
         const std::size_t n_reads = (std::size_t)(r1 - r0), n_haps = (std::size_t)(h1 - h0);
         if (n_reads != reads.size()) throw std::runtime_error("B200RegionBatcher: reads vector differs from the one added");
-        std::vector<std::vector<double>> out(n_reads, std::vector<double>(n_haps));
-        if (n_reads == 0 || n_haps == 0) return out;
+        if (n_reads == 0 || n_haps == 0) return std::vector<std::vector<double>>(n_reads, std::vector<double>(n_haps));
         double* flat = b.lik.data() + b.out_beg[w.region];
         std::vector<int32_t> read_len(n_reads);
         for (std::size_t r = 0; r < n_reads; r++) read_len[r] = b.read_off[r0 + r + 1] - b.read_off[r0 + r];
         std::vector<uint8_t> keep(n_reads);
         phmm_normalize_filter(flat, (int32_t)n_reads, (int32_t)n_haps, read_len.data(), keep.data());   // :24-46
+        std::vector<std::vector<double>> out;
+        out.reserve(n_reads);
         std::size_t k = 0;
         for (std::size_t r = 0; r < n_reads; r++) {
             if (!keep[r]) continue;
-            out[k].assign(flat + r * n_haps, flat + (r + 1) * n_haps);
+            out.emplace_back(flat + r * n_haps, flat + (r + 1) * n_haps);       // one allocation per surviving row
             if (k != r) reads[k] = std::move(reads[r]);
             ++k;
         }
-        out.resize(k);
         reads.erase(reads.begin() + k, reads.end());
         return out;
     }

@@ -160,7 +160,7 @@ void do_work_batched(hc::HaplotypeCaller& caller, int n_threads, std::size_t reg
     }
     // pass 2: every region with more than one haplotype goes to the device, batched across windows
 #ifdef HC_DEVICE_GL
-    hc::B200RegionBatcher batcher((int64_t)2e9, 4096, 3, /*device_gl=*/true);
+    hc::B200RegionBatcher batcher((int64_t)1.6e10, 4096, 3, /*device_gl=*/true);
     for (auto& w : windows)
         if (!w.reads.empty() && w.haplotypes.size() > 1) { plan_sites(w); w.region_id = batcher.add_region(w.haplotypes, w.reads, w.sites); }
 #else
