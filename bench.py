@@ -738,8 +738,8 @@ def main():
         if rank == 0:
             try:
                 in_process = in_process_section(pkg, world, args, s5_pre)
-            except Exception as ex:                                # reported, and fails the run below
-                in_process = {"ok": False, "error": f"{type(ex).__name__}: {ex}"}
+            except Exception as ex:                                # an infrastructure problem is reported, not counted as a
+                in_process = {"ok": None, "error": f"{type(ex).__name__}: {ex}"}    # parity failure (only ok == False fails the run)
         dist.barrier(group=host_group)
 
     failed = not all_ok
@@ -799,7 +799,7 @@ def main():
         }
         if in_process is not None:
             line["in_process"] = in_process
-            failed |= not in_process.get("ok", False)
+            failed |= in_process.get("ok") is False
         if world == 1 and not args.no_chrm:
             try:
                 line["e2e_chrm"] = e2e_chrm_section(pkg)

@@ -148,7 +148,9 @@ public:
     void reserve(std::size_t n)
     {
         if (n <= cap_) return;
-        std::size_t want = std::max<std::size_t>(n + n / 2, (std::size_t)1 << 20);
+        // page-locking is slow (of the order of a millisecond per megabyte) and growing means doing it again: start at
+        // 4 MB (a 1.6e10-cell batch of 150-base reads is about that) and double
+        std::size_t want = std::max<std::size_t>(std::max(n, 2 * cap_), (std::size_t)4 << 20);
         void* q = nullptr;
         int rc = phmm_host_alloc(want, &q);
         if (rc != PHMM_OK) throw std::runtime_error(std::string("phmm_host_alloc: ") + phmm_strerror(rc));
@@ -293,7 +295,13 @@ public:
                                bool device_gl = false)
         : flush_cells_(flush_cells), flush_regions_(flush_regions), max_in_flight_(max_in_flight), device_gl_(device_gl),
           eng_(B200Engine::get()) {}
-    ~B200RegionBatcher() { try { drain(); } catch (...) {} }
+    ~B200RegionBatcher()
+    {
+        try { drain(); } catch (...) {}
+        // page-locked slabs outlive the batcher: the next one (a new contig, a new chunk of windows) starts warm
+        std::lock_guard<std::mutex> lk(slab_pool_mu());
+        for (auto& sl : free_slabs_) if (sl && slab_pool().size() < 8) slab_pool().push_back(std::move(sl));
+    }
     B200RegionBatcher(const B200RegionBatcher&) = delete;
     B200RegionBatcher& operator=(const B200RegionBatcher&) = delete;
 
@@ -317,7 +325,11 @@ public:
         if (!cur_) {
             cur_ = std::make_unique<Pending>();
             if (!free_slabs_.empty()) { cur_->slab = std::move(free_slabs_.back()); free_slabs_.pop_back(); }
-            else cur_->slab = std::make_unique<Slabs>();
+            else {
+                std::lock_guard<std::mutex> lk(slab_pool_mu());
+                if (!slab_pool().empty()) { cur_->slab = std::move(slab_pool().back()); slab_pool().pop_back(); }
+            }
+            if (!cur_->slab) cur_->slab = std::make_unique<Slabs>();
         }
         Pending& b = *cur_;
         Slabs& sl = *b.slab;
@@ -458,6 +470,9 @@ private:
         B200PinnedBytes read_bases, read_q, hap_bases;
         void clear() { read_bases.clear(); read_q.clear(); hap_bases.clear(); }
     };
+    // process-wide pool of idle slabs (never destructed: page-locked memory must not be freed after the CUDA runtime)
+    static std::mutex& slab_pool_mu() { static std::mutex* m = new std::mutex(); return *m; }
+    static std::vector<std::unique_ptr<Slabs>>& slab_pool() { static auto* v = new std::vector<std::unique_ptr<Slabs>>(); return *v; }
     struct Pending {
         std::vector<int32_t> region_read_beg, region_hap_beg, read_off, hap_off;
         std::vector<int64_t> out_beg;
