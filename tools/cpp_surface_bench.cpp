@@ -77,7 +77,7 @@ int main(int argc, char** argv)
         std::printf("{\"regions\": %d, \"cells\": %.4e, \"batcher_gcups\": %.1f, \"batcher_s\": %.4f, \"per_region_call_gcups\": %.1f, "
                     "\"per_region_call_ms\": %.3f, \"reads_kept_last\": %lld, "
                     "\"what\": \"S3 regions held as one std::string per read / haplotype; (a) hc::B200RegionBatcher add_region + take "
-                    "(gather into page-locked slabs, cross-region batches of 2e9 cells, 3 in flight, cap + filter + row erase on the way out), "
+                    "(gather into page-locked slabs, cross-region batches of 1.6e10 cells, 3 in flight, cap + filter + row erase on the way out), "
                     "(b) hc::B200PairHMM::compute_likelihoods, one synchronous call per region\"}\n",
                     n_regions, cells, cells / best / 1e9, best, cells_pw / best_pw / 1e9, 1e3 * best_pw / std::min(per_window_regions, n_regions), kept);
     } catch (const std::exception& e) {
