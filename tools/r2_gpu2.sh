@@ -3,7 +3,7 @@
 TAG=${1:-r2c}; N=${2:-2}
 mkdir -p gpurun_out; O=gpurun_out/$TAG
 nvidia-smi -L > ${O}_gpus.txt
-python -m pytest tests -m gpu -x -q -k "multi_device or sharded" > ${O}_pytest.log 2>&1; echo "pytest rc=$?" >> ${O}_pytest.log
+python -m pytest tests -m gpu -x -q -k "multi_device or sharded or full_size or pinned_inputs" > ${O}_pytest.log 2>&1; echo "pytest rc=$?" >> ${O}_pytest.log
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 20 --warmup 3 > ${O}_bench_n$N.json 2> ${O}_bench_n$N.err; echo "bench rc=$?" >> ${O}_bench_n$N.err
 PHMM_TRACE_INIT=1 python -c "
 import time; t=time.perf_counter()
