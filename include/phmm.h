@@ -243,7 +243,9 @@ int  phmm_plan(const phmm_batch* b, int32_t sm_count, int32_t host_threads, phmm
  * Device-resident form, used by bench.py for the "inputs already in HBM" number:
  * phmm_stage uploads and plans once, phmm_run_staged launches the forward + rescue kernels
  * `iters` times back to back and returns the mean device time per iteration (CUDA events on the
- * launching stream), phmm_fetch_staged brings the results of the last run back.
+ * launching stream), phmm_fetch_staged brings the results of the last run back.  The device-resident form lives on
+ * the engine's FIRST device (devices[0]): it is the measuring instrument of one GPU, the multi-device scheduler is
+ * phmm_submit / phmm_wait.
  */
 typedef struct phmm_staged phmm_staged;
 int  phmm_stage(phmm_engine* e, const phmm_batch* b, phmm_staged** out);
