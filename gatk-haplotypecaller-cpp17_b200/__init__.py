@@ -43,7 +43,7 @@ def build(verbose=False):
 class _Options(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("n_devices", C.c_int32), ("devices", C.POINTER(C.c_int32)),
                 ("pipeline_depth", C.c_int32), ("exact_fp32", C.c_int32), ("host_threads", C.c_int32),
-                ("use_double", C.c_int32), ("fp64_first", C.c_int32), ("reserved", C.c_int32 * 1)]
+                ("use_double", C.c_int32), ("fp64_first", C.c_int32), ("recurrence", C.c_int32)]
 
 
 class _Batch(C.Structure):
@@ -472,7 +472,7 @@ class Result:
 class PairHMMEngine:
     """Owns one phmm_engine (streams, memory pool, worker per device)."""
 
-    def __init__(self, devices=None, pipeline_depth=2, exact_fp32=False, host_threads=1, use_double=False, fp64_first=0):
+    def __init__(self, devices=None, pipeline_depth=2, exact_fp32=False, host_threads=1, use_double=False, fp64_first=0, recurrence=0):
         self._L = lib()
         opt = _Options()
         opt.struct_size = C.sizeof(_Options)
@@ -482,6 +482,7 @@ class PairHMMEngine:
         opt.devices = C.cast(self._dev_arr, C.POINTER(C.c_int32))
         opt.pipeline_depth, opt.exact_fp32, opt.host_threads = pipeline_depth, int(exact_fp32), host_threads
         opt.fp64_first = int(fp64_first)                # 0 auto, 1 never, 2 always (include/phmm.h)
+        opt.recurrence = int(recurrence)                # 0 scaled recurrence where applicable, 1 reference operation order
         opt.use_double = int(use_double)                # the reference's g_use_double (intel_pairhmm.hpp:58,71,135)
         self._h = C.c_void_p()
         rc = self._L.phmm_create(C.byref(opt), C.byref(self._h))

@@ -43,7 +43,7 @@ namespace {
 
 constexpr size_t kAlign = 256;
 constexpr int kSmemBytesPerWarpBudget = 8 * 1024;    // haplotype stream share of the per-warp shared memory
-constexpr int kPerHapTableBytes = 8 + 4 + 4 + 4;     // init_y, haplotype index, stream position, length
+constexpr int kPerHapTableBytes = 3 * 8 + 4 + 4 + 4; // init_y, two scales (MODE 3), haplotype index, stream position, length
 inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 
 struct KernelTable {
@@ -340,6 +340,7 @@ struct DeviceCtx {
     float last_rescue_frac = 0.f;        // share of pairs the previous batch redid in FP64
     int fp64_first_opt = 0;              // phmm_options.fp64_first
     bool device_log10 = false;           // phmm_engine::device_log10
+    bool scaled_recurrence = true;       // phmm_options.recurrence == 0
     std::unique_ptr<HostPool> pool;      // host_threads - 1 helpers for this device's worker thread
     std::unique_ptr<HostPool> pack_pool; // helpers of the PACKER thread (its copies must not queue behind the worker's
                                          // planning and finalizing in the same pool: a HostPool runs one parallel_for at a time)
@@ -1120,6 +1121,9 @@ int stage_launch(DeviceCtx& dc, Slot& s, bool exact, bool use_double, bool do_la
         int rcp = plan_part(&view, 0, n_regions, out0, dc.sm_count, dc.last_rescue_frac, pool, p, plan, err, dc.fp64_first_opt);
         if (rcp) return rcp;
         p.g0 = g0; p.g1 = g1; p.out0 = out0; p.read0 = c.read0;
+        // constant gap penalties with i == d: the lane-aligned jobs take the scaled recurrence (six FP32-pipe
+        // instructions per cell) unless the engine was asked for the reference's operation order
+        if (p.mode == kModeConstShared && !exact && dc.scaled_recurrence) p.mode = kModeConstScaled;
     }
     const std::vector<LongPair>& long_pairs = plan.long_pairs;
     const std::vector<WarpJob>* jobs_k = plan.jobs_k;
@@ -1172,6 +1176,8 @@ int stage_launch(DeviceCtx& dc, Slot& s, bool exact, bool use_double, bool do_la
         a.cg_f[3] = T.ph2pr_f[gd]; a.cg_f[4] = T.ph2pr_f[gc];
         a.cg_d[0] = T.mm_d[mmi]; a.cg_d[1] = 1.0 - T.ph2pr_d[gc]; a.cg_d[2] = T.ph2pr_d[gi];
         a.cg_d[3] = T.ph2pr_d[gd]; a.cg_d[4] = T.ph2pr_d[gc];
+        a.gs_f = a.cg_f[1] * a.cg_f[2];                      // MODE 3: pGAPM * pMX, one rounding in each precision
+        a.gs_d = a.cg_d[1] * a.cg_d[2];
     }
     a.hap_bases = dp + o_haps;
     a.ph2pr_f = dc.d_ph2pr_f; a.mm_f = dc.d_mm_f; a.ph2pr_d = dc.d_ph2pr_d; a.mm_d = dc.d_mm_d;
@@ -1715,6 +1721,7 @@ int phmm_create(const phmm_options* opt, phmm_engine** out)
         dc->pack_pool.reset(new HostPool(std::max(0, e->host_threads - 1)));
         dc->fp64_first_opt = e->opt.fp64_first;
         dc->device_log10 = e->device_log10;
+        dc->scaled_recurrence = e->opt.recurrence == 0 && getenv("PHMM_REFERENCE_ORDER") == nullptr;
         const auto tid = std::chrono::steady_clock::now();
         int rc = init_device(*dc, depth, err);
         if (trace_init) fprintf(stderr, "phmm init trace: device %d context + tables + %d slots %.1f ms\n", dc->ordinal, depth, since(tid));

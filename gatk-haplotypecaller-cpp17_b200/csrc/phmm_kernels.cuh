@@ -127,6 +127,9 @@ struct KernelArgs {
     // MODE 1/2: batch-constant transition factors {pMM, pGAPM, pMX, pMY, pXX(=pYY)} per precision
     float  cg_f[5];
     double cg_d[5];
+    // MODE 3 (scaled recurrence): pGAPM * pMX, rounded once on the host in each precision
+    float  gs_f;
+    double gs_d;
     // work list
     const WarpJob* jobs;
     int32_t n_jobs;
@@ -208,6 +211,9 @@ struct PolicyF32x2 {
     __device__ static __forceinline__ const S* ph2pr(const KernelArgs& a) { return a.ph2pr_f; }
     __device__ static __forceinline__ const S* mm(const KernelArgs& a) { return a.mm_f; }
     __device__ static __forceinline__ S cg(const KernelArgs& a, int i) { return a.cg_f[i]; }
+    __device__ static __forceinline__ S gs(const KernelArgs& a) { return a.gs_f; }
+    __device__ static __forceinline__ S kScaleHeadroom() { return 0.015625f; }           // 2^-6: row 0 of the scaled recurrence <= 2^126
+    __device__ static __forceinline__ S smul(S a, S b) { return __fmul_rn(a, b); }
 };
 
 struct PolicyF64 {
@@ -240,6 +246,9 @@ struct PolicyF64 {
     __device__ static __forceinline__ const S* ph2pr(const KernelArgs& a) { return a.ph2pr_d; }
     __device__ static __forceinline__ const S* mm(const KernelArgs& a) { return a.mm_d; }
     __device__ static __forceinline__ S cg(const KernelArgs& a, int i) { return a.cg_d[i]; }
+    __device__ static __forceinline__ S gs(const KernelArgs& a) { return a.gs_d; }
+    __device__ static __forceinline__ S kScaleHeadroom() { return 0.25; }                // 2^-2: row 0 <= 2^1022
+    __device__ static __forceinline__ S smul(S a, S b) { return __dmul_rn(a, b); }
 };
 
 // Shared-memory loads by 32-bit shared address (keeps each cursor in ONE register; the generic
@@ -283,7 +292,19 @@ constexpr int kStreamNext = 0x80, kStreamIdle = 0x81, kStreamNext2 = 0x82;   // 
 // FP64 (rescue): group g redoes job.read[2g] and then job.read[2g+1], each only for the haplotypes
 // whose raw FP32 result is below 1e-28f (intel_pairhmm.hpp:137); it reads that decision straight
 // from args.raw32 (and a per-(job,chunk) flag byte), so no work list is built between the kernels.
-enum : int { kModeGeneral = 0, kModeConst = 1, kModeConstShared = 2 };
+// MODE 3, the SCALED recurrence (constant gap penalties with i == d, fast engines only, every layout -- so that a
+// pair's bits do not depend on which kernel its batch happened to put it in): carry X^ = X / pMX and Y^ = Y / pMY
+// instead of X and Y (in fact (s M, X / s2, Y / s2) with s s2 = pMX, the split chosen per haplotype so that nothing
+// overflows or eats the underflow guard: see where s_inity is filled).  Then
+//     M[r][c]  = prior * (pMM * M[r-1][c-1] + g * (X^[r-1][c-1] + Y^[r-1][c-1])),   g = pGAPM * pMX  (= pGAPM * pMY)
+//     X^[r][c] = M[r-1][c] + pXX * X^[r-1][c]          Y^[r][c] = M[r][c-1] + pYY * Y^[r][c-1]
+// -- the products M * pMX and M * pMY are gone: SIX FP32-pipe instructions per cell (mul, fma, fma, mul, fma, fma)
+// instead of the eight of the reference's expression (seven in MODE 2), the M * p array of MODE 2 and its K register
+// pairs too; the final sum is sum(M) + pMX * sum(X^).  Same recurrence in exact arithmetic; in floating point it
+// rounds differently from the reference's operation order (as the FMA-contracted MODE 2 already does), well inside
+// the 1e-4 bar on the final log10 -- measured, with the number of rescue decisions it moves at the threshold, in
+// DESIGN.md section 4.1.  Row 0 of the reference (Y = INITIAL_CONSTANT / haplen) becomes Y^ = that / pMY.
+enum : int { kModeGeneral = 0, kModeConst = 1, kModeConstShared = 2, kModeConstScaled = 3 };
 
 #ifndef PHMM_MIN_WARPS
 #define PHMM_MIN_WARPS 16      // resident warps per SM the small-K constant-gap FP32 kernels are held to
@@ -323,6 +344,8 @@ forward_kernel(const KernelArgs args)
     constexpr int NG = 32 / G;
     constexpr bool CONSTG = MODE != kModeGeneral;
     constexpr bool SHARED = MODE == kModeConstShared;
+    constexpr bool SCALED = MODE == kModeConstScaled;
+    static_assert(!SCALED || !EXACT, "the scaled recurrence exists for the fast kernels (exact = the reference's operation order)");
     constexpr int KP = CONSTG ? 1 : K;    // per-row factor arrays collapse to one warp-uniform entry
     constexpr int SUBT = subtable_bytes(K, G);
     constexpr int LANE_B = lane_units(K) * 16;
@@ -391,7 +414,9 @@ forward_kernel(const KernelArgs args)
     uint8_t* sb   = smem + (size_t)warp * args.smem_bytes_per_warp;
     uint8_t* stab = sb + args.stream_cap;
     S*   s_inity  = reinterpret_cast<S*>(stab + tables_bytes(K, G));
-    int* s_hidx   = reinterpret_cast<int*>(s_inity + args.haps_per_job);
+    S*   s_s2     = s_inity + args.haps_per_job;       // SCALED: per-haplotype scale of X^, Y^ and 1 / (scale of M^)
+    S*   s_invs   = s_s2 + args.haps_per_job;
+    int* s_hidx   = reinterpret_cast<int*>(s_invs + args.haps_per_job);
     int* s_apos   = s_hidx + args.haps_per_job;
     int* s_alen   = s_apos + args.haps_per_job;
     V* const my_tab = reinterpret_cast<V*>(stab + (PACKED ? 0 : grp) * 5 * SUBT + (PACKED ? lane : l) * LANE_B);   // + b * SUBT, [k]
@@ -427,7 +452,7 @@ forward_kernel(const KernelArgs args)
         V pXXc = P::splat(0);             // MODE 1/2: X self-transition of every row
         int pad[NH];
         if (CONSTG) {
-            pMM[0] = P::splat(P::cg(args, 0)); pGAPM[0] = P::splat(P::cg(args, 1));
+            pMM[0] = P::splat(P::cg(args, 0)); pGAPM[0] = P::splat(SCALED ? P::gs(args) : P::cg(args, 1));
             pMX[0] = P::splat(P::cg(args, 2)); pMY[0] = P::splat(P::cg(args, 3));
             pXXc   = P::splat(P::cg(args, 4));
         }
@@ -525,6 +550,18 @@ forward_kernel(const KernelArgs args)
                 sb[pos + H] = (uint8_t)kStreamNext;
                 if (ZRESET) sb[pos + H + 1] = (uint8_t)kStreamNext2;
                 s_inity[n] = P::sdiv(P::init_const(), (S)H);   // avx-pairhmm-template.h:86
+                if (SCALED) {
+                    // The scaled state is (M^, X^, Y^) = (s M, X / s2, Y / s2) with s s2 = pMX: the recurrence is
+                    // homogeneous, so the split only shows in row 0 (Y^ = Y / s2) and in the final sum.  s2 = pMX would
+                    // put row 0 at 2^120 / (H pMX) -- beyond FLT_MAX for the reference's 'I' -- so s2 is the smallest
+                    // scale that keeps row 0 at or below 2^126 (2^1022 in FP64): s2 = max(pMX, 1 / (64 H)); M^ then sits
+                    // at most ~3 decades lower than the reference's M, well inside the 10 decades between the rescue
+                    // threshold and the smallest normal float.
+                    const S s2 = max(P::cg(args, 2), P::sdiv(P::kScaleHeadroom(), (S)H));
+                    s_inity[n] = P::sdiv(s_inity[n], s2);
+                    s_s2[n] = s2;
+                    s_invs[n] = P::sdiv(s2, P::cg(args, 2));   // 1 / s
+                }
                 s_hidx[n] = h; s_apos[n] = pos; s_alen[n] = H;
             }
             pos += H + 1 + (ZRESET ? 1 : 0); ++n;
@@ -598,7 +635,7 @@ forward_kernel(const KernelArgs args)
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const int kk = CONSTG ? 0 : k;
-                const V yv = SHARED ? Pm[k] : MUL(M[k], pMY[kk]);
+                const V yv = SCALED ? M[k] : SHARED ? Pm[k] : MUL(M[k], pMY[kk]);     // SCALED: Y^ = M(c-1) + pYY Y^(c-1)
                 const V cYY = ALIGNED ? fYY : pYY[ALIGNED ? 0 : k];
                 Y[k] = EXACT ? P::addx(yv, MUL(Y[k], cYY)) : P::fma(Y[k], cYY, yv);
             }
@@ -614,9 +651,9 @@ forward_kernel(const KernelArgs args)
                 const int kk = CONSTG ? 0 : k;
                 const V cXX = (k == 0) ? pXX0 : (CONSTG ? pXXc : pYY[ALIGNED ? 0 : k]);
                 const V uX = k ? X[k - 1] : inX;            // (row-1, c)
-                V um;                                       // M(row-1, c) * pMX(row)
-                if (k == 0) um = MUL(inM, pMX0);
-                else um = SHARED ? Pm[k - 1] : MUL(M[k - 1], pMX[kk]);
+                V um;                                       // M(row-1, c) * pMX(row); SCALED: M(row-1, c) itself
+                if (k == 0) um = SCALED ? inM : MUL(inM, pMX0);
+                else um = SCALED ? M[k - 1] : SHARED ? Pm[k - 1] : MUL(M[k - 1], pMX[kk]);
                 X[k] = EXACT ? P::addx(um, MUL(uX, cXX)) : P::fma(uX, cXX, um);
             }
             // last row of the last lane is the last read row: running sums (:328-343)
@@ -632,6 +669,9 @@ forward_kernel(const KernelArgs args)
             const V outY = (ALIGNED && !PACKED) ? P::sel(dummy_lane[0], dummy_lane[NH - 1], P::splat(inity_cur), Y[K - 1]) : Y[K - 1];
             V rM = P::shfl_up(M[K - 1], G), rX = P::shfl_up(X[K - 1], G), rY = P::shfl_up(outY, G);
             if (PACKED) rY = P::sel(top, top, P::splat(inity_cur), rY);
+            // SCALED: there is no product with pMX0 = 0 left to annihilate what the top lane receives (another group's
+            // last row, or -- the shuffle has no source for lane 0 -- its own)
+            if (SCALED && (PACKED || !ALIGNED)) rM = P::sel(top, top, P::splat(0), rM);
             if (kSkew == 2) {
                 inM = qM; inX = qX; inY = qY;
                 qM = rM; qX = rX; qY = rY;
@@ -650,7 +690,8 @@ forward_kernel(const KernelArgs args)
                     if (!P::kIsF32) w = w && needs_redo(args.raw32[oi]);
                     if (P::kIsF32 && LIST) w = w && __float_as_uint(args.raw32[oi]) == kNeedsF32;    // selective pass
                     if (!w) continue;
-                    const S res = P::sadd(P::get(sumM, hf), P::get(sumX, hf));
+                    const S res = SCALED ? P::sadd(P::smul(P::get(sumM, hf), s_invs[jcur]), P::smul(P::get(sumX, hf), s_s2[jcur]))
+                                         : P::sadd(P::get(sumM, hf), P::get(sumX, hf));     // SCALED: sum(M^) / s + s2 sum(X^)
                     if (P::kIsF32) {
                         args.raw32[oi] = (float)res;
                         if ((float)res < kMinAccepted) { if (LIST) flag_or(my_flag, kFlagRedo64); else *my_flag = (uint8_t)kFlagRedo64; }

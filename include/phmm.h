@@ -81,7 +81,12 @@ typedef struct phmm_options {
                                    does not prove the underflow (identical log10 values and rescue decisions;
                                    the optional raw32 output of a proven underflow is 0.0f).  1: never.  2: always.
                                    Ignored (never) with exact_fp32, whose raw FP32 sums are part of the contract. */
-    int32_t reserved[1];
+    int32_t recurrence;         /* arithmetic of the default (non-exact) FP32 / FP64 kernels for constant gap penalties
+                                   with i == d -- the reference's only case.  0: the SCALED recurrence where the layout
+                                   allows it (carries X / pMX and Y / pMY: six FP32-pipe instructions per cell instead
+                                   of seven; same mathematics, different rounding, well inside 1e-4 on the log10).
+                                   1: the reference's operation order, FMA-contracted (round 1's kernels).
+                                   exact_fp32 overrides both.  Environment: PHMM_REFERENCE_ORDER=1 forces 1. */
 } phmm_options;
 
 /*
