@@ -54,7 +54,8 @@ sys.path.insert(0, ROOT)
 METRIC = "pairhmm_gcups"
 UNIT = "GCUPS"
 SM_LANES = 128          # FP32 lanes per SM
-INSTR_PER_CELL = 8      # FP32-pipe instructions per cell with FMA
+INSTR_PER_CELL = 8      # FP32-pipe instructions per cell with FMA: the roofline's definition of a cell
+INSTR_PER_CELL_SCALED = 6   # what the default engine's scaled recurrence executes per cell (phmm_kernels.cuh: MODE 3)
 DEPTH = 4               # batches in flight on the e2e path
 
 
@@ -786,6 +787,12 @@ def main():
                          "peak_def": f"{sms} SMs x {SM_LANES} FP32 lanes x {sm_max_mhz:.0f} MHz / {INSTR_PER_CELL} FP32-pipe instr per cell "
                                      "(max SM clock of MEASURED_PEAKS.json; not HBM-bound: 7.6e-4 B/cell)",
                          "peak_at_clock": round(peak_clk, 1), "frac_at_clock": round(per_gpu / peak_clk, 4),
+                         "executed_form": None if (args.exact or args.workload == "s3g") else {
+                             "instr_per_cell": INSTR_PER_CELL_SCALED, "peak": round(peak * INSTR_PER_CELL / INSTR_PER_CELL_SCALED, 1),
+                             "frac": round(per_gpu / (peak * INSTR_PER_CELL / INSTR_PER_CELL_SCALED), 4),
+                             "what": "the default engine carries X / pMX and Y / pMY (scaled recurrence): 6 FP32-pipe instructions per cell "
+                                     "instead of the 8 of the reference's expression that `peak` assumes, so `frac` can exceed 1; this is the "
+                                     "fraction of the issue-rate bound of the recurrence actually executed"},
                          "kernel": ("the FP32 forward launch of the batch (forward_kernel<PolicyF32x2, ...>), timed alone with CUDA events "
                                     "on its stream, in-library (phmm_run_staged_ex)") if single_launch else
                                    "all forward launches of a step (several shapes on forked streams), CUDA events in-library",

@@ -657,7 +657,7 @@ int launch_kernels(Slot& s, bool exact, int tier_lo, int tier_hi, std::string& e
             }
     if (normal_pass) {
         if (p.n_long) {      // reads beyond one lane-group pass: all precision tiers inside one launch
-            launch_long_reads(a, s.d_long, p.n_long, p.mode == kModeGeneral, exact, use_double, s.stream);
+            launch_long_reads(a, s.d_long, p.n_long, p.mode == kModeGeneral || p.mode == kModeGeneralScaled, exact, use_double, s.stream);
             CUDA_TRY(cudaGetLastError());
             p.launches++;
         }
@@ -1099,6 +1099,22 @@ int stage_pack(DeviceCtx& dc, Slot& s, const phmm_batch* b, int g0, int g1, int6
 
 int launch_genotype_part(DeviceCtx& dc, Slot& s, std::string& err);
 
+// The scaled recurrence for per-base gap penalties (MODE 4) carries X / pMX_r: stepping from row r-1 to row r multiplies
+// X^ by pXX_r pMX_{r-1} / pMX_r, which is harmless as long as the gap-open bytes of a batch do not spread by more than
+// the gap-continuation penalty absorbs.  Conservative test over the whole part (bytes & 127, as the kernel reads
+// them): continuation penalty >= 10 (pXX <= 0.1) and spread(i) - min(c) <= 10, i.e. that factor is <= 10 everywhere.
+bool scaled_general_is_safe(const phmm_batch& v)
+{
+    if (!v.read_i || !v.read_d || !v.read_c || v.n_reads == 0) return false;
+    const size_t n = (size_t)v.read_off[v.n_reads];
+    int imin = 127, imax = 0, dmin = 127, dmax = 0, cmin = 127;
+    for (size_t k = 0; k < n; k++) {
+        const int i = v.read_i[k] & 127, d = v.read_d[k] & 127, c = v.read_c[k] & 127;
+        imin = std::min(imin, i); imax = std::max(imax, i); dmin = std::min(dmin, d); dmax = std::max(dmax, d); cmin = std::min(cmin, c);
+    }
+    return cmin >= 10 && (imax - imin) - cmin <= 10 && (dmax - dmin) - cmin <= 10;
+}
+
 int stage_launch(DeviceCtx& dc, Slot& s, bool exact, bool use_double, bool do_launch, std::string& err)
 {
     s.device_log10 = dc.device_log10;
@@ -1124,6 +1140,7 @@ int stage_launch(DeviceCtx& dc, Slot& s, bool exact, bool use_double, bool do_la
         // constant gap penalties with i == d: the lane-aligned jobs take the scaled recurrence (six FP32-pipe
         // instructions per cell) unless the engine was asked for the reference's operation order
         if (p.mode == kModeConstShared && !exact && dc.scaled_recurrence) p.mode = kModeConstScaled;
+        if (p.mode == kModeGeneral && !exact && dc.scaled_recurrence && scaled_general_is_safe(view)) p.mode = kModeGeneralScaled;
     }
     const std::vector<LongPair>& long_pairs = plan.long_pairs;
     const std::vector<WarpJob>* jobs_k = plan.jobs_k;

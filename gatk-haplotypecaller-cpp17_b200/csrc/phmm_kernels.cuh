@@ -304,7 +304,12 @@ constexpr int kStreamNext = 0x80, kStreamIdle = 0x81, kStreamNext2 = 0x82;   // 
 // rounds differently from the reference's operation order (as the FMA-contracted MODE 2 already does), well inside
 // the 1e-4 bar on the final log10 -- measured, with the number of rescue decisions it moves at the threshold, in
 // DESIGN.md section 4.1.  Row 0 of the reference (Y = INITIAL_CONSTANT / haplen) becomes Y^ = that / pMY.
-enum : int { kModeGeneral = 0, kModeConst = 1, kModeConstShared = 2, kModeConstScaled = 3 };
+// MODE 4 is the same idea for PER-BASE gap penalties: row r carries X^ = X / pMX_r and Y^ = Y / pMY_r, its five
+// register-resident factors become pMM_r, pGAPM_r pMX_{r-1}, pGAPM_r pMY_{r-1}, pXX_r pMX_{r-1} / pMX_r and pYY_r, and
+// the final sum is sum(M) + pMX_R sum(X^).  M itself is unscaled and the reference's row 0 keeps its own Y
+// (its "pMY" is taken as 1), so nothing moves towards overflow or underflow as long as neighbouring rows' gap-open
+// penalties do not differ by more than the engine checks for (phmm_engine.cu: scaled_general_is_safe).
+enum : int { kModeGeneral = 0, kModeConst = 1, kModeConstShared = 2, kModeConstScaled = 3, kModeGeneralScaled = 4 };
 
 #ifndef PHMM_MIN_WARPS
 #define PHMM_MIN_WARPS 16      // resident warps per SM the small-K constant-gap FP32 kernels are held to
@@ -328,7 +333,7 @@ template <class P, int K, int G, int MODE, bool EXACT, bool ALIGNED, bool PACKED
 __global__ void __launch_bounds__(kWarpsPerCta * 32, (P::kIsF32 && K <= 5 && MODE != kModeGeneral) ? PHMM_MIN_WARPS / kWarpsPerCta : 1)
 forward_kernel(const KernelArgs args)
 {
-    static_assert(!ALIGNED || MODE != kModeGeneral, "ALIGNED needs batch-constant gap penalties");
+    static_assert(!ALIGNED || (MODE != kModeGeneral && MODE != kModeGeneralScaled), "ALIGNED needs batch-constant gap penalties");
     static_assert(!PACKED || (ALIGNED && G == 32), "PACKED is a variant of ALIGNED on the whole warp");
     // ZRESET (the lane-aligned layouts): a lane does not RESET its registers between two haplotypes, it runs
     // two ordinary cell steps with its transition factors zeroed (stream bytes NEXT, NEXT2).  The recurrence
@@ -342,9 +347,11 @@ forward_kernel(const KernelArgs args)
     using V = typename P::V;
     constexpr int NH = P::NH;
     constexpr int NG = 32 / G;
-    constexpr bool CONSTG = MODE != kModeGeneral;
+    constexpr bool CONSTG = MODE != kModeGeneral && MODE != kModeGeneralScaled;
     constexpr bool SHARED = MODE == kModeConstShared;
-    constexpr bool SCALED = MODE == kModeConstScaled;
+    constexpr bool SCALEDC = MODE == kModeConstScaled;        // scaled recurrence, constant gap penalties
+    constexpr bool SCALEDG = MODE == kModeGeneralScaled;      // scaled recurrence, per-base gap penalties
+    constexpr bool SCALED = SCALEDC || SCALEDG;
     static_assert(!SCALED || !EXACT, "the scaled recurrence exists for the fast kernels (exact = the reference's operation order)");
     constexpr int KP = CONSTG ? 1 : K;    // per-row factor arrays collapse to one warp-uniform entry
     constexpr int SUBT = subtable_bytes(K, G);
@@ -452,7 +459,7 @@ forward_kernel(const KernelArgs args)
         V pXXc = P::splat(0);             // MODE 1/2: X self-transition of every row
         int pad[NH];
         if (CONSTG) {
-            pMM[0] = P::splat(P::cg(args, 0)); pGAPM[0] = P::splat(SCALED ? P::gs(args) : P::cg(args, 1));
+            pMM[0] = P::splat(P::cg(args, 0)); pGAPM[0] = P::splat(SCALEDC ? P::gs(args) : P::cg(args, 1));
             pMX[0] = P::splat(P::cg(args, 2)); pMY[0] = P::splat(P::cg(args, 3));
             pXXc   = P::splat(P::cg(args, 4));
         }
@@ -485,6 +492,15 @@ forward_kernel(const KernelArgs args)
                             mx_  = ph2pr[gi];
                             my_  = ph2pr[gd];
                             yy   = ph2pr[gc];
+                            if (SCALEDG) {
+                                // the row above: the read's previous base, or the reference's row 0 (factors taken as 1)
+                                const S pmx_up = ri > 0 ? ph2pr[args.read_i[ro + ri - 1] & 127] : P::one();
+                                const S pmy_up = ri > 0 ? ph2pr[args.read_d[ro + ri - 1] & 127] : P::one();
+                                const S own_mx = mx_;
+                                mx_  = P::smul(gapm, pmy_up);                         // slot of pMX: weight of Y^ above-left
+                                my_  = P::sdiv(P::smul(yy, pmx_up), own_mx);          // slot of pMY: X^ self-transition
+                                gapm = P::smul(gapm, pmx_up);                         // weight of X^ above-left
+                            }
                         } else {
                             yy = P::cg(args, 4);
                         }
@@ -517,7 +533,7 @@ forward_kernel(const KernelArgs args)
         // (the last lane of another read's group) shuffles down: two more zeroed factors for the diagonal.
         const bool top = (l == 0);
         const V pMX0 = top ? P::splat(0) : pMX[0];
-        const V pXX0 = top ? P::splat(0) : (CONSTG ? pXXc : pYY[0]);
+        const V pXX0 = top ? P::splat(0) : (CONSTG ? pXXc : SCALEDG ? pMY[0] : pYY[0]);
         const V pMM0   = (PACKED && top) ? P::splat(0) : pMM[0];
         const V pGAPX0 = (PACKED && top) ? P::splat(0) : pGAPM[0];
         bool dummy_lane[NH];              // ALIGNED: this lane holds only dummy rows of packed read hf
@@ -550,7 +566,7 @@ forward_kernel(const KernelArgs args)
                 sb[pos + H] = (uint8_t)kStreamNext;
                 if (ZRESET) sb[pos + H + 1] = (uint8_t)kStreamNext2;
                 s_inity[n] = P::sdiv(P::init_const(), (S)H);   // avx-pairhmm-template.h:86
-                if (SCALED) {
+                if (SCALEDC) {
                     // The scaled state is (M^, X^, Y^) = (s M, X / s2, Y / s2) with s s2 = pMX: the recurrence is
                     // homogeneous, so the split only shows in row 0 (Y^ = Y / s2) and in the final sum.  s2 = pMX would
                     // put row 0 at 2^120 / (H pMX) -- beyond FLT_MAX for the reference's 'I' -- so s2 is the smallest
@@ -623,7 +639,7 @@ forward_kernel(const KernelArgs args)
                 // NEXT / NEXT2 / idle bytes of the straddling loop)
                 const V cMM = (PACKED && k == 0) ? fMM0 : (ZRESET ? fMM : pMM[kk]);
                 const V cGX = (PACKED && k == 0) ? fGX0 : (ZRESET ? fG : pGAPM[kk]);
-                const V cGY = ZRESET ? fG : pGAPM[kk];
+                const V cGY = ZRESET ? fG : SCALEDG ? pMX[kk] : pGAPM[kk];
                 if (EXACT) {
                     // reference operation order, unfused (avx-pairhmm-template.h:188)
                     t0[k] = P::addx(P::addx(MUL(dM, cMM), MUL(dX, cGX)), MUL(dY, cGY));
@@ -649,7 +665,7 @@ forward_kernel(const KernelArgs args)
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const int kk = CONSTG ? 0 : k;
-                const V cXX = (k == 0) ? pXX0 : (CONSTG ? pXXc : pYY[ALIGNED ? 0 : k]);
+                const V cXX = (k == 0) ? pXX0 : (CONSTG ? pXXc : SCALEDG ? pMY[kk] : pYY[ALIGNED ? 0 : k]);
                 const V uX = k ? X[k - 1] : inX;            // (row-1, c)
                 V um;                                       // M(row-1, c) * pMX(row); SCALED: M(row-1, c) itself
                 if (k == 0) um = SCALED ? inM : MUL(inM, pMX0);
@@ -690,8 +706,10 @@ forward_kernel(const KernelArgs args)
                     if (!P::kIsF32) w = w && needs_redo(args.raw32[oi]);
                     if (P::kIsF32 && LIST) w = w && __float_as_uint(args.raw32[oi]) == kNeedsF32;    // selective pass
                     if (!w) continue;
-                    const S res = SCALED ? P::sadd(P::smul(P::get(sumM, hf), s_invs[jcur]), P::smul(P::get(sumX, hf), s_s2[jcur]))
-                                         : P::sadd(P::get(sumM, hf), P::get(sumX, hf));     // SCALED: sum(M^) / s + s2 sum(X^)
+                    S res;
+                    if (SCALEDC) res = P::sadd(P::smul(P::get(sumM, hf), s_invs[jcur]), P::smul(P::get(sumX, hf), s_s2[jcur]));   // sum(M^) / s + s2 sum(X^)
+                    else if (SCALEDG) res = P::sadd(P::get(sumM, hf), P::smul(P::get(sumX, hf), ph2pr[args.read_i[args.read_off[rd[hf] + 1] - 1] & 127]));
+                    else res = P::sadd(P::get(sumM, hf), P::get(sumX, hf));
                     if (P::kIsF32) {
                         args.raw32[oi] = (float)res;
                         if ((float)res < kMinAccepted) { if (LIST) flag_or(my_flag, kFlagRedo64); else *my_flag = (uint8_t)kFlagRedo64; }

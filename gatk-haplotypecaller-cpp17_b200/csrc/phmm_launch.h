@@ -54,7 +54,7 @@ struct GenotypeArgs {
 void launch_genotype(const GenotypeArgs& g, const float* lik32, const RescueOut* rescue, const unsigned* rescue_count,
                      double log10_init_d, int sm_count, cudaStream_t st);
 
-constexpr int kNumModes = 4;      // 3 = the scaled recurrence (fast engines; the exact kernels of that slot are the mode-2 ones)
+constexpr int kNumModes = 5;      // 3 = the scaled recurrence (fast engines; the exact kernels of that slot are the mode-2 ones)
 // tab[mode][aligned][shape][list]; aligned = every read length of the job is a multiple of K (constant-gap
 // modes only; the general mode has no aligned variant and its [1] row repeats [0]); list = the launch pulls its
 // units from a work list (phmm_kernels.cuh: LIST) -- compiled for the fast engines only (nullptr otherwise: the
@@ -74,17 +74,20 @@ inline void register_shape(KernelTab& tab)
     constexpr int L = LIST ? 1 : 0;
     if constexpr (S >= kFirstPackedShape) {          // PACKED: lane-aligned kernels of the constant-gap modes only
         tab[0][0][S][L] = nullptr; tab[0][1][S][L] = nullptr; tab[1][0][S][L] = nullptr; tab[2][0][S][L] = nullptr; tab[3][0][S][L] = nullptr;
+        tab[4][0][S][L] = nullptr; tab[4][1][S][L] = nullptr;
         tab[1][1][S][L] = forward_kernel<P, K, G, 1, EXACT, true, true, LIST>;
         tab[2][1][S][L] = forward_kernel<P, K, G, 2, EXACT, true, true, LIST>;
         if constexpr (EXACT) tab[3][1][S][L] = tab[2][1][S][L];
         else tab[3][1][S][L] = forward_kernel<P, K, G, 3, EXACT, true, true, LIST>;
     } else {
-        if constexpr (EXACT) {                       // (the exact engines never select mode 3; tier 3 of a mode-3 part does)
+        if constexpr (EXACT) {                       // (the exact engines never select modes 3 / 4; tier 3 of such a part does)
             tab[3][0][S][L] = forward_kernel<P, K, G, 2, EXACT, false, false, LIST>;
             tab[3][1][S][L] = forward_kernel<P, K, G, 2, EXACT, true, false, LIST>;
+            tab[4][0][S][L] = tab[4][1][S][L] = forward_kernel<P, K, G, 0, EXACT, false, false, LIST>;
         } else {
             tab[3][0][S][L] = forward_kernel<P, K, G, 3, EXACT, false, false, LIST>;
             tab[3][1][S][L] = forward_kernel<P, K, G, 3, EXACT, true, false, LIST>;
+            tab[4][0][S][L] = tab[4][1][S][L] = forward_kernel<P, K, G, 4, EXACT, false, false, LIST>;
         }
         tab[0][0][S][L] = tab[0][1][S][L] = forward_kernel<P, K, G, 0, EXACT, false, false, LIST>;
         tab[1][0][S][L] = forward_kernel<P, K, G, 1, EXACT, false, false, LIST>;

@@ -483,3 +483,28 @@ def test_hunt_for_a_fast_vs_exact_rescue_flip(pkg, engine, exact_engine):
         total_near += int(near.sum()); total_flips += int(flips2.sum())
     print(f"rescue-flip hunt: {total_near} pairs within 2 ulp of the threshold examined, {total_flips} rescue decisions flipped by FMA contraction")
     assert total_near >= 20                                            # the hunt really reached the threshold
+
+
+@pytest.mark.parametrize("name,make", [
+    ("S3", lambda s: s.s3(2)),
+    ("S2 (packed lane groups)", lambda s: s.s2(8)),
+    ("S5 ragged windows", lambda s: s.s5_batch(48, seed=5)),
+    ("S4 all rescued", lambda s: s.s4(2, n_reads=24, n_haps=4)),
+    ("tiny haplotypes, every length", lambda s: s.random_small(71, n_regions=30, max_reads=12, max_haps=4, max_read_len=255, max_hap_len=40, general_gaps=False)),
+])
+def test_scaled_and_reference_order_recurrences_agree(pkg, engine, oracle, name, make):
+    """The default engine runs the SCALED recurrence for constant gap penalties with i == d (phmm_kernels.cuh MODE 3:
+    six FP32-pipe instructions per cell); phmm_options.recurrence = 1 keeps the reference's operation order
+    (FMA-contracted, MODE 2).  Both must meet the oracle's bar, take the same rescue decisions on these inputs, and
+    agree with each other far inside it; haplotypes of a few bases exercise the per-haplotype scale split (row 0 of the
+    scaled recurrence must neither overflow nor push M towards the underflow guard)."""
+    b = make(pkg.synth)
+    want = oracle.batch(b, threads=16)
+    got = engine.compute(b)
+    check(got, want, what=name + " scaled")
+    with pkg.PairHMMEngine(devices=[0], recurrence=1) as ref_order:
+        other = ref_order.compute(b)
+    check(other, want, what=name + " reference order")
+    keep = ~want["rescued"].astype(bool)
+    assert _maxerr(got.log10[keep], other.log10[keep]) <= 2e-5
+    assert _maxerr(got.log10[~keep], other.log10[~keep]) <= 1e-9
