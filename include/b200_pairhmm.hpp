@@ -49,6 +49,8 @@ namespace hc
 //                          guarantee; the default (FMA-contracted) mode agrees to <= 1e-4 log10 and can in
 //                          principle flip a `raw < 1e-28f` rescue decision or a GQ rounding.
 //   PHMM_USE_DOUBLE=1      the reference's g_use_double switch (intel_pairhmm.hpp:58,71,135)
+//   PHMM_REFERENCE_ORDER=1 (read by the library) the default engine's arithmetic in the reference's operation order,
+//                          FMA-contracted, instead of the scaled recurrence (include/phmm.h: phmm_options.recurrence)
 //   PHMM_HOST_THREADS=n    host threads per device for planning / packing / finalizing (default 4)
 class B200Engine
 {
