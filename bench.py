@@ -302,7 +302,7 @@ def helper_parity(npz_path):
     z = np.load(npz_path)
     n = int(z["n_slices"])
     e32 = e64 = 0.0
-    mism = pairs = n_resc = 0
+    mism = pairs = n_resc = flips = 0
     for k in range(n):
         g = lambda name: z[f"s{k}_{name}"]
         kw = {}
@@ -314,7 +314,16 @@ def helper_parity(npz_path):
         want = oracle.batch(b, threads=os.cpu_count() or 1)
         got, got_resc = g("log10"), g("rescued").astype(bool)
         resc = want["rescued"].astype(bool)
-        mism += int((got_resc != resc).sum())
+        diff = got_resc != resc
+        if diff.any():
+            # a rescue decision may legitimately differ only AT the threshold (raw FP32 sum within a few ulp of 1e-28f,
+            # intel_pairhmm.hpp:137: the fast arithmetic rounds differently from the reference's) and then the two
+            # values still agree to the FP32 tolerance; anything else is a mismatch
+            thr = np.float32(1e-28).view(np.int32).astype(np.int64)
+            ulps = np.abs(want["raw32"].view(np.int32).astype(np.int64) - thr)
+            fine = diff & (ulps <= 16) & (np.abs(got - want["log10"]) <= 1e-4)
+            flips += int(fine.sum())
+            mism += int((diff & ~fine).sum())
         both32, both64 = ~resc & ~got_resc, resc & got_resc
         if both32.any():
             e32 = max(e32, float(np.abs(got[both32] - want["log10"][both32]).max()))
@@ -326,7 +335,7 @@ def helper_parity(npz_path):
         pairs += b.n_pairs
         n_resc += int(resc.sum())
     ok = mism == 0 and e32 <= 1e-4 and e64 <= 1e-9
-    print(json.dumps({"max_abs_fp32": e32, "max_abs_fp64": e64, "rescue_mismatches": mism, "regions_checked": n,
+    print(json.dumps({"max_abs_fp32": e32, "max_abs_fp64": e64, "rescue_mismatches": mism, "rescue_flips_at_threshold": flips, "regions_checked": n,
                       "pairs_checked": pairs, "rescued_pairs_checked": n_resc, "tolerance": "1e-4 fp32 / 1e-9 fp64-rescued",
                       "checker": "oracle/liboracle.so (subprocess)", "ok": bool(ok)}))
 

@@ -30,7 +30,9 @@
 //     every ~2.2 (register-file read ports: ~2 32-bit reads/lane/clk; profiles/r01_microbench_pipes.txt).
 //     MODE 2 (i == d) additionally shares the product M*p between X of the row below and Y of the
 //     next column (7 instead of 8 FP32-pipe instructions per cell, bit-identical results).
-//     MODE 0 is the general per-base path (per-row factors in registers).
+//     MODE 0 is the general per-base path (per-row factors in registers).  MODE 3 / MODE 4 (round 2, the fast
+//     engines' default) are the SCALED forms of MODE 2 / MODE 0: X / pMX and Y / pMY are carried instead of X and Y,
+//     which removes both M * p products -- six FP32-pipe instructions per cell; see the comment at the MODE enum.
 //   * reads are right-aligned in the K*G row block: missing rows at the top are DUMMY rows that
 //     reproduce row 0 of the reference (M = X = 0, Y = INITIAL_CONSTANT/haplen,
 //     avx-pairhmm-template.h:86-92,161-175) exactly (priors 0, Y self-transition 1), so the last
@@ -42,9 +44,10 @@
 //     pairs that end near the double denormal range (kFlushDanger).  Reads beyond 255 bases take
 //     phmm_long.cu.
 //
-// Arithmetic: default is FMA-contracted (8 FP32-pipe instructions per cell: the roofline unit of
-// SURVEY.md section 8d); EXACT=true uses unfused mul/add in the reference's operation order and
-// is bit-identical to the reference's raw results.  FP32 is flush-to-zero (intel_pairhmm.hpp:102-105).
+// Arithmetic: FMA-contracted, in the reference's operation order (MODE 0/1/2: 8 / 8 / 7 FP32-pipe instructions per
+// cell; 8 is the roofline unit of SURVEY.md section 8d) or as the scaled recurrence (MODE 3/4: 6); EXACT=true uses
+// unfused mul/add in the reference's operation order and is bit-identical to the reference's raw results.  FP32 is
+// flush-to-zero (intel_pairhmm.hpp:102-105).
 #pragma once
 #include <cstdint>
 #include <type_traits>
