@@ -1139,7 +1139,9 @@ int stage_launch(DeviceCtx& dc, Slot& s, bool exact, bool use_double, bool do_la
         p.g0 = g0; p.g1 = g1; p.out0 = out0; p.read0 = c.read0;
         // constant gap penalties with i == d: the lane-aligned jobs take the scaled recurrence (six FP32-pipe
         // instructions per cell) unless the engine was asked for the reference's operation order
-        if (p.mode == kModeConstShared && !exact && dc.scaled_recurrence) p.mode = kModeConstScaled;
+        // (not for gap-open penalties beyond Q96: M^ = s M with s = min(1, 64 H pMX) must stay a normal float wherever
+        //  M matters, i.e. down to ~1e-30 of the 2^120 scale, which needs H pMX >= 2e-10; the reference's 'I' is 5e-8)
+        if (p.mode == kModeConstShared && !exact && dc.scaled_recurrence && (p.gap[0] & 127) <= 96) p.mode = kModeConstScaled;
         if (p.mode == kModeGeneral && !exact && dc.scaled_recurrence && scaled_general_is_safe(view)) p.mode = kModeGeneralScaled;
     }
     const std::vector<LongPair>& long_pairs = plan.long_pairs;

@@ -508,3 +508,26 @@ def test_scaled_and_reference_order_recurrences_agree(pkg, engine, oracle, name,
     keep = ~want["rescued"].astype(bool)
     assert _maxerr(got.log10[keep], other.log10[keep]) <= 2e-5
     assert _maxerr(got.log10[~keep], other.log10[~keep]) <= 1e-9
+
+
+@pytest.mark.parametrize("gap", [(40, 40, 35), (96, 96, 43), (100, 100, 43), (127, 127, 60), (33, 33, 43), (73, 73, 12)])
+def test_scaled_recurrence_over_the_range_of_constant_gap_penalties(pkg, engine, oracle, gap):
+    """The scale split of the scaled recurrence depends on the gap-open probability (row 0 must not overflow, M^ must
+    not underflow): from a cheap gap (Q40 raw byte: s = 1) over the reference's own 'I' to penalties beyond Q96, where
+    the engine keeps the reference-order kernels; short and long haplotypes."""
+    rng = np.random.default_rng(sum(gap))
+    alpha = np.frombuffer(b"ACGT", np.uint8)
+    regions = []
+    for H in (3, 40, 700):
+        hap = alpha[rng.integers(0, 4, H)]
+        reads, quals = [], []
+        for rl in (1, 7, 33, 100, 150, 151, 255):
+            o = int(rng.integers(0, max(1, H - rl + 1)))
+            r = np.resize(hap[o:o + rl], rl).copy()
+            m = rng.random(rl) < 0.05; r[m] = alpha[rng.integers(0, 4, int(m.sum()))]
+            reads.append(r); quals.append((33 + rng.integers(2, 42, rl)).astype(np.uint8))
+        regions.append((reads, quals, [hap, hap[::-1].copy()]))
+    b0 = pkg.Batch.from_regions(regions)
+    b = pkg.Batch(b0.region_read_beg, b0.region_hap_beg, b0.read_off, b0.read_bases, b0.read_q, b0.hap_off, b0.hap_bases,
+                  gap_open_i=gap[0], gap_open_d=gap[1], gap_cont_c=gap[2])
+    check(engine.compute(b), oracle.batch(b, threads=8), what=f"gap bytes {gap}")
