@@ -84,7 +84,7 @@ EXPORTS = ["phmm_create", "phmm_destroy", "phmm_compute", "phmm_submit", "phmm_w
            "phmm_last_error", "phmm_abi_version", "phmm_normalize_filter", "phmm_tables",
            "phmm_stage", "phmm_run_staged", "phmm_run_staged_ex", "phmm_run_staged_pipelined",
            "phmm_fetch_staged", "phmm_free_staged", "phmm_plan", "phmm_sw_align", "phmm_host_register",
-           "phmm_host_unregister", "phmm_host_alloc", "phmm_host_free", "phmm_submit_gl", "phmm_wait_gl", "phmm_jacobian_table", "phmm_sw_release", "phmm_debug_check"]
+           "phmm_host_unregister", "phmm_host_alloc", "phmm_host_free", "phmm_submit_gl", "phmm_wait_gl", "phmm_jacobian_table", "phmm_sw_release", "phmm_debug_check", "phmm_validate"]
 
 class _PlanInfo(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("mode", C.c_int32), ("n_jobs", C.c_int32), ("n_long_pairs", C.c_int32),
@@ -195,6 +195,7 @@ def lib():
         L.phmm_host_unregister.argtypes = [C.c_void_p]
         L.phmm_submit_gl.argtypes = [C.c_void_p, C.POINTER(_Batch), C.POINTER(_Sites), C.POINTER(C.c_int64)]
         L.phmm_wait_gl.argtypes = [C.c_void_p, C.c_int64, C.POINTER(_GlResult)]
+        L.phmm_validate.argtypes = [C.POINTER(_Batch), C.POINTER(_Sites)]
         L.phmm_jacobian_table.argtypes = [C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.c_int32)]
         L.phmm_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
         L.phmm_host_free.argtypes = [C.c_void_p]
@@ -216,6 +217,13 @@ def host_tables():
     L.phmm_tables(C.byref(pf), C.byref(mf), C.byref(pd), C.byref(md), C.byref(n))
     return {"ph2pr_f32": np.ctypeslib.as_array(pf, (128,)).copy(), "mm_f32": np.ctypeslib.as_array(mf, (n.value,)).copy(),
             "ph2pr_f64": np.ctypeslib.as_array(pd, (128,)).copy(), "mm_f64": np.ctypeslib.as_array(md, (n.value,)).copy()}
+
+
+def validate(batch, sites=None):
+    """phmm_validate: the status code phmm_submit / phmm_submit_gl would refuse the arguments with (0 = fine); no device."""
+    cb = batch.c_struct()
+    cs = sites.c_struct() if sites is not None else None
+    return int(lib().phmm_validate(C.byref(cb), C.byref(cs) if cs is not None else None))
 
 
 def jacobian_table():

@@ -1915,6 +1915,15 @@ int phmm_submit_gl(phmm_engine* e, const phmm_batch* b, const phmm_sites* sites,
     return submit_impl(e, b, sites, t);
 }
 
+int phmm_validate(const phmm_batch* b, const phmm_sites* sites)
+{
+    // the checks phmm_submit / phmm_submit_gl make before anything touches a device (pure host logic)
+    std::string err;
+    int rc = validate_batch(b, err);
+    if (rc || !sites) return rc;
+    return validate_sites(b, sites, err);
+}
+
 int phmm_jacobian_table(const double** table, int32_t* n)
 {
     int k = 0;

@@ -203,6 +203,8 @@ typedef struct phmm_gl_result {
 } phmm_gl_result;
 int  phmm_submit_gl(phmm_engine* e, const phmm_batch* b, const phmm_sites* sites, phmm_ticket* t);
 int  phmm_wait_gl(phmm_engine* e, phmm_ticket t, phmm_gl_result* r);
+/* The argument checks of phmm_submit (sites == NULL) / phmm_submit_gl, on their own: pure host logic, no device. */
+int  phmm_validate(const phmm_batch* b, const phmm_sites* sites);
 /* The Jacobian-logarithm table the reduction indexes (utils/math_utils.hpp:17-29), for tests. */
 int  phmm_jacobian_table(const double** table, int32_t* n);
 

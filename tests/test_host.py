@@ -171,3 +171,21 @@ def test_planner_chunks_follow_the_makespan_model(pkg):
     assert info["haps_per_job"] <= 3
     info, _ = pkg.plan(S.s3(1))
     assert info["haps_per_job"] == 1 and info["hap_chunks"] == 16          # few jobs: every haplotype its own unit
+
+
+def test_argument_checks_without_a_device(pkg):
+    """phmm_validate: what phmm_submit / phmm_submit_gl refuse before touching a device (include/phmm.h error codes)."""
+    S, B = pkg.synth, pkg.Batch
+    b = S.random_small(3, n_regions=4, max_reads=6, max_haps=3, general_gaps=False)
+    assert pkg.validate(b) == 0
+    assert pkg.validate(B.from_regions([([b""], [b""], [b"ACGT"])])) == 1                      # empty read
+    assert pkg.validate(B.from_regions([([np.full(2049, 65, np.uint8)], [np.full(2049, 70, np.uint8)], [b"ACGT"])])) == 5
+    nh, nr = b.haps_per_region, b.reads_per_region
+    ok = [(g, 2, np.zeros(int(nh[g]), np.uint8), np.ones(int(nr[g]), np.uint8)) for g in range(b.n_regions)]
+    assert pkg.validate(b, pkg.Sites(b, ok)) == 0
+    assert pkg.validate(b, pkg.Sites(b, ok[::-1])) == 1                                          # regions must be non-decreasing
+    bad_allele = [(0, 2, np.full(int(nh[0]), 2, np.uint8), None)]
+    assert pkg.validate(b, pkg.Sites(b, bad_allele)) == 1                                        # allele 2 of a 2-allele site
+    too_many = [(0, 8, np.zeros(int(nh[0]), np.uint8), None)]
+    assert pkg.validate(b, pkg.Sites(b, too_many)) == 1                                          # > PHMM_MAX_ALLELES
+    assert pkg.validate(b, pkg.Sites(b, [])) == 0
