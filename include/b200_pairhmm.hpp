@@ -266,7 +266,8 @@ struct B200PairHMM
 // assembling.  take() returns exactly what B200PairHMM::compute_likelihoods would have returned for
 // that region -- capped rows, poorly modelled reads erased from the caller's vector
 // (intel_pairhmm.hpp:24-46) -- so the genotyper consumes it unchanged.  Regions may be taken in any
-// order, each once.  One thread calls add_region()/take() (the engine has one submitter).
+// order, each ONCE (a second take throws): the batch's result storage is released with its last region.
+// One thread calls add_region()/take() (the engine has one submitter).
 // One variant site of a region for the DEVICE-SIDE genotype reduction (phmm_submit_gl):
 // what Genetyper::assign_genotype_likelihoods knows about the site before it looks at a likelihood
 // (genotyper/genotyper.hpp:381-388): the allele count, the allele every haplotype carries (get_haplotype_mapper)
@@ -324,6 +325,8 @@ public:
     int add_region(const std::vector<HaplotypeT>& haps, const std::vector<ReadT>& reads)
     {
         if (device_gl_ && !pending_sites_) throw std::runtime_error("B200RegionBatcher: a device_gl batcher takes regions with their sites");
+        for (const auto& r : reads)           // checked before anything is appended: a refused region leaves the batch as it was
+            if (r.SEQ.size() != r.QUAL.size()) throw std::runtime_error("B200RegionBatcher: SEQ and QUAL lengths differ");
         if (!cur_) {
             cur_ = std::make_unique<Pending>();
             if (!free_slabs_.empty()) { cur_->slab = std::move(free_slabs_.back()); free_slabs_.pop_back(); }
@@ -339,7 +342,6 @@ public:
         if (b.region_read_beg.empty()) { b.region_read_beg.push_back(0); b.region_hap_beg.push_back(0); b.read_off.push_back(0); b.hap_off.push_back(0); b.out_beg.push_back(0); }
         int64_t read_bytes = 0, hap_bytes = 0;
         for (const auto& r : reads) {
-            if (r.SEQ.size() != r.QUAL.size()) throw std::runtime_error("B200RegionBatcher: SEQ and QUAL lengths differ");
             sl.read_bases.append(r.SEQ.data(), r.SEQ.size());       // gathered straight into page-locked memory
             sl.read_q.append(r.QUAL.data(), r.QUAL.size());
             b.read_off.push_back((int32_t)sl.read_bases.size());
@@ -417,12 +419,15 @@ public:
         if (region_id < 0 || region_id >= (int)where_.size()) throw std::runtime_error("B200RegionBatcher: unknown region id");
         const Where w = where_[region_id];
         if (w.batch == next_batch_id_) flush();                          // still under construction
-        Pending& b = *batches_.at((size_t)(w.batch - first_batch_id_));
-        while (!b.done) wait_oldest();
+        Pending& b = *batches_.at((size_t)w.batch);
+        if (b.region_read_beg.empty()) throw std::runtime_error("B200RegionBatcher: region taken twice");
         const int32_t r0 = b.region_read_beg[w.region], r1 = b.region_read_beg[w.region + 1];
         const int32_t h0 = b.region_hap_beg[w.region], h1 = b.region_hap_beg[w.region + 1];
         const std::size_t n_reads = (std::size_t)(r1 - r0), n_haps = (std::size_t)(h1 - h0);
         if (n_reads != reads.size()) throw std::runtime_error("B200RegionBatcher: reads vector differs from the one added");
+        mark_taken(b, w.region);
+        while (!b.done) wait_oldest();
+        Releaser release_when_done{&b};
         if (n_reads == 0 || n_haps == 0) return std::vector<std::vector<double>>(n_reads, std::vector<double>(n_haps));
         double* flat = b.lik.data() + b.out_beg[w.region];
         std::vector<int32_t> read_len(n_reads);
@@ -449,8 +454,10 @@ public:
         if (region_id < 0 || region_id >= (int)where_.size()) throw std::runtime_error("B200RegionBatcher: unknown region id");
         const Where w = where_[region_id];
         if (w.batch == next_batch_id_) flush();
-        Pending& b = *batches_.at((size_t)(w.batch - first_batch_id_));
+        Pending& b = *batches_.at((size_t)w.batch);
+        mark_taken(b, w.region);
         while (!b.done) wait_oldest();
+        Releaser release_when_done{&b};
         B200RegionGL out;
         const int32_t s0 = b.region_site_beg[w.region], s1 = b.region_site_beg[w.region + 1];
         for (int32_t k = s0; k < s1; k++) {
@@ -485,11 +492,34 @@ private:
         std::vector<uint8_t> hap_allele, read_overlap, read_keep;
         std::vector<int64_t> gl_off;
         std::vector<double> gl;
+        std::vector<uint8_t> taken;           // per region: handed out already
+        int32_t n_taken = 0;
         int64_t cells = 0;
         phmm_ticket ticket = 0;
         bool submitted = false, done = false;
     };
     struct Where { int batch; int32_t region; };
+
+    // every region is taken exactly once; the batch's storage goes when the last one has been
+    static void mark_taken(Pending& b, int32_t region)
+    {
+        if (b.region_read_beg.empty()) throw std::runtime_error("B200RegionBatcher: region taken twice");   // released batch
+        const std::size_t n = b.region_read_beg.size() - 1;
+        if (b.taken.size() != n) b.taken.assign(n, 0);
+        if (b.taken[(std::size_t)region]) throw std::runtime_error("B200RegionBatcher: region taken twice");
+        b.taken[(std::size_t)region] = 1;
+        ++b.n_taken;
+    }
+    struct Releaser {                          // runs when take()/take_gl() return: a whole-genome run must not keep every matrix
+        Pending* b;
+        ~Releaser()
+        {
+            if (b->n_taken != (int32_t)(b->region_read_beg.size() - 1)) return;
+            Pending fresh;
+            fresh.submitted = b->submitted; fresh.done = b->done; fresh.ticket = b->ticket;
+            *b = std::move(fresh);             // vectors freed; the shell stays so that batch ids keep indexing batches_
+        }
+    };
 
     void wait_oldest()
     {
@@ -529,7 +559,7 @@ private:
     std::vector<std::unique_ptr<Slabs>> free_slabs_;
     std::deque<std::unique_ptr<Pending>> batches_;
     std::vector<Where> where_;
-    int next_batch_id_ = 0, first_batch_id_ = 0;
+    int next_batch_id_ = 0;
     int in_flight_ = 0;
 };
 

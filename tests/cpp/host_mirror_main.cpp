@@ -72,6 +72,10 @@ int main(int argc, char** argv)
                 print(reads[i], lik);
             }
             std::fprintf(stderr, "batches %d\n", batcher.batches_submitted);
+            // every region is handed out once (its batch's storage is released with the last one)
+            bool refused = false;
+            try { if (n) (void)batcher.take(ids[0], reads[0]); } catch (const std::runtime_error&) { refused = true; }
+            if (n && !refused) { std::fprintf(stderr, "error: a second take of region 0 was not refused\n"); return 2; }
         } catch (const std::exception& e) {
             std::fprintf(stderr, "error: %s\n", e.what());
             return 1;
