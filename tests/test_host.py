@@ -20,6 +20,25 @@ def test_library_exports_every_declared_symbol(pkg):
     assert L.phmm_abi_version() == 1
 
 
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/phmm.h must compile as C99 (what cgo / JNI / ctypes-style bindings see), and a C
+    translation unit that names every entry point must link against the library."""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "phmm.h")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr], check=True)
+    names = re.findall(r"^\s*(?:const\s+char\*|int64_t|int|void)\s+(phmm_\w+)\s*\(", open(hdr).read(), re.M)
+    src = tmp_path / "link_all.c"
+    src.write_text('#include "phmm.h"\n#include <stdio.h>\nint main(void) {\n  void* f[] = {' +
+                   ", ".join(f"(void*)(size_t){n}" for n in names) +
+                   '};\n  printf("%d %d\\n", (int)(sizeof f / sizeof f[0]), phmm_abi_version());\n  return 0;\n}\n')
+    libdir = os.path.join(ROOT, "gatk-haplotypecaller-cpp17_b200")
+    exe = tmp_path / "link_all"
+    subprocess.run(["gcc", "-std=c99", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L" + libdir, "-lphmm_b200", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert int(out[0]) == len(names) and int(out[1]) == 1
+
+
 def test_only_sm100a_code_in_the_library(pkg):
     import subprocess
     out = subprocess.run(["cuobjdump", "-lelf", pkg.LIB_PATH], capture_output=True, text=True).stdout
