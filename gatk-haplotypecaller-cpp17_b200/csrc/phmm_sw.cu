@@ -292,11 +292,10 @@ extern "C" int phmm_sw_align(int32_t device, const phmm_sw_batch* b, phmm_sw_res
         ctx = slot.get();
     }
     std::lock_guard<std::mutex> lk(ctx->mu);
-    if (!ctx->stream) {
-        SW_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-        SW_TRY(cudaEventCreate(&ctx->e0));
-        SW_TRY(cudaEventCreate(&ctx->e1));
-    }
+    // (each object on its own: a call that failed half-way through this block is completed by the next one)
+    if (!ctx->stream) SW_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    if (!ctx->e0) SW_TRY(cudaEventCreate(&ctx->e0));
+    if (!ctx->e1) SW_TRY(cudaEventCreate(&ctx->e1));
     cudaStream_t st = ctx->stream;
 
     // the aligner's all-match shortcut on the host; everything else grouped by columns-per-lane class
