@@ -1,7 +1,7 @@
 #!/bin/bash
 # GPU pass: parity tests, the bench line, every shape's throughput, launch lists + full-set ncu summaries
 # (the .ncu-rep files are summarised ON the box by tools/ncu_summary.py and deleted: gpurun_out is capped at 64 MiB).
-# usage: r2_gpu_pass.sh <tag> [steps...]   steps: pytest bench shapes launches ncu_s4 ncu_s3g ncu_s5 ncu_s3
+# usage: r2_gpu_pass.sh <tag> [steps...]   steps: pytest bench shapes launches ncu_s4 ncu_s3g ncu_s5 ncu_s3 ncu_s2
 TAG=$1; shift
 STEPS="${@:-pytest bench shapes launches ncu_s4 ncu_s3g}"
 mkdir -p gpurun_out
@@ -28,6 +28,7 @@ full() {  # name, skip, count, cmd...
 if has ncu_s4; then full s4 20 6 python tools/prof_s3.py 64 s4; fi
 if has ncu_s3g; then full s3g 4 2 python tools/prof_s3.py 128 s3g; fi
 if has ncu_s3; then full s3 4 2 python tools/prof_s3.py 128 s3; fi
+if has ncu_s2; then full s2 4 2 python tools/prof_s3.py 256 s2; fi
 if has ncu_s5; then full s5 48 4 python tools/prof_s5.py 1024; fi
 du -sh gpurun_out; ls -la gpurun_out
 if has mode0exp; then
