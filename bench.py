@@ -55,7 +55,7 @@ METRIC = "pairhmm_gcups"
 UNIT = "GCUPS"
 SM_LANES = 128          # FP32 lanes per SM
 INSTR_PER_CELL = 8      # FP32-pipe instructions per cell with FMA: the roofline's definition of a cell
-INSTR_PER_CELL_SCALED = 6   # what the default engine's scaled recurrence executes per cell (phmm_kernels.cuh: MODE 3)
+INSTR_PER_CELL_SCALED = 5   # what the default engine's scaled, pMM-folded recurrence executes per cell (phmm_kernels.cuh: MODE 3, FOLD)
 DEPTH = 4               # batches in flight on the e2e path
 
 
@@ -799,7 +799,7 @@ def main():
                          "executed_form": None if (args.exact or args.workload == "s3g") else {
                              "instr_per_cell": INSTR_PER_CELL_SCALED, "peak": round(peak * INSTR_PER_CELL / INSTR_PER_CELL_SCALED, 1),
                              "frac": round(per_gpu / (peak * INSTR_PER_CELL / INSTR_PER_CELL_SCALED), 4),
-                             "what": "the default engine carries X / pMX and Y / pMY (scaled recurrence): 6 FP32-pipe instructions per cell "
+                             "what": "the default engine carries X / pMX and Y / pMY and folds pMM into the priors (scaled recurrence): 5 FP32-pipe instructions per cell "
                                      "instead of the 8 of the reference's expression that `peak` assumes, so `frac` can exceed 1; this is the "
                                      "fraction of the issue-rate bound of the recurrence actually executed"},
                          "kernel": ("the FP32 forward launch of the batch (forward_kernel<PolicyF32x2, ...>), timed alone with CUDA events "

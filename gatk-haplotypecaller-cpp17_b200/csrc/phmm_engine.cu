@@ -1112,7 +1112,8 @@ bool scaled_general_is_safe(const phmm_batch& v)
         const int i = v.read_i[k] & 127, d = v.read_d[k] & 127, c = v.read_c[k] & 127;
         imin = std::min(imin, i); imax = std::max(imax, i); dmin = std::min(dmin, d); dmax = std::max(dmax, d); cmin = std::min(cmin, c);
     }
-    return cmin >= 10 && (imax - imin) - cmin <= 10 && (dmax - dmin) - cmin <= 10;
+    // (imin, dmin >= 10: pMM >= 0.8 on every row -- the kernel divides the row's gap weights by it)
+    return cmin >= 10 && imin >= 10 && dmin >= 10 && (imax - imin) - cmin <= 10 && (dmax - dmin) - cmin <= 10;
 }
 
 int stage_launch(DeviceCtx& dc, Slot& s, bool exact, bool use_double, bool do_launch, std::string& err)
@@ -1141,7 +1142,9 @@ int stage_launch(DeviceCtx& dc, Slot& s, bool exact, bool use_double, bool do_la
         // instructions per cell) unless the engine was asked for the reference's operation order
         // (not for gap-open penalties beyond Q96: M^ = s M with s = min(1, 64 H pMX) must stay a normal float wherever
         //  M matters, i.e. down to ~1e-30 of the 2^120 scale, which needs H pMX >= 2e-10; the reference's 'I' is 5e-8)
-        if (p.mode == kModeConstShared && !exact && dc.scaled_recurrence && (p.gap[0] & 127) <= 96) p.mode = kModeConstScaled;
+        // (and not below Q10: the scaled kernels fold pMM into the priors and divide the gap weights by it; pMM >= 0.8 there,
+        //  while it reaches 0 for gap-open penalties below Q4)
+        if (p.mode == kModeConstShared && !exact && dc.scaled_recurrence && (p.gap[0] & 127) <= 96 && (p.gap[0] & 127) >= 10) p.mode = kModeConstScaled;
         if (p.mode == kModeGeneral && !exact && dc.scaled_recurrence && scaled_general_is_safe(view)) p.mode = kModeGeneralScaled;
     }
     const std::vector<LongPair>& long_pairs = plan.long_pairs;
@@ -1195,8 +1198,8 @@ int stage_launch(DeviceCtx& dc, Slot& s, bool exact, bool use_double, bool do_la
         a.cg_f[3] = T.ph2pr_f[gd]; a.cg_f[4] = T.ph2pr_f[gc];
         a.cg_d[0] = T.mm_d[mmi]; a.cg_d[1] = 1.0 - T.ph2pr_d[gc]; a.cg_d[2] = T.ph2pr_d[gi];
         a.cg_d[3] = T.ph2pr_d[gd]; a.cg_d[4] = T.ph2pr_d[gc];
-        a.gs_f = a.cg_f[1] * a.cg_f[2];                      // MODE 3: pGAPM * pMX, one rounding in each precision
-        a.gs_d = a.cg_d[1] * a.cg_d[2];
+        a.gs_f = a.cg_f[1] * a.cg_f[2] / a.cg_f[0];          // MODE 3: g' = pGAPM * pMX / pMM (pMM is folded into the priors)
+        a.gs_d = a.cg_d[1] * a.cg_d[2] / a.cg_d[0];
     }
     a.hap_bases = dp + o_haps;
     a.ph2pr_f = dc.d_ph2pr_f; a.mm_f = dc.d_mm_f; a.ph2pr_d = dc.d_ph2pr_d; a.mm_d = dc.d_mm_d;

@@ -285,7 +285,8 @@ __device__ __forceinline__ int base_code(uint8_t b) {
 // units, so the 8 lanes of an LDS.128 quarter-warp hit 8 distinct bank groups.
 __host__ __device__ constexpr int lane_units(int K) { return (((K + 1) / 2) % 2) ? (K + 1) / 2 : (K + 1) / 2 + 1; }
 __host__ __device__ constexpr int subtable_bytes(int K, int G) { return (G * lane_units(K) * 16 + 127) / 128 * 128; }
-__host__ __device__ constexpr int tables_bytes(int K, int G) { return (32 / G) * 5 * subtable_bytes(K, G); }
+constexpr int kZeroRowBytes = 128;      // a row of zero priors behind the tables (the folded recurrence's zero steps read it)
+__host__ __device__ constexpr int tables_bytes(int K, int G) { return (32 / G) * 5 * subtable_bytes(K, G) + kZeroRowBytes; }
 constexpr int kStreamNext = 0x80, kStreamIdle = 0x81, kStreamNext2 = 0x82;   // stream bytes >= 0x80 are not columns
 
 // ---- the forward kernel ----------------------------------------------------------------------
@@ -355,6 +356,11 @@ forward_kernel(const KernelArgs args)
     constexpr bool SCALEDC = MODE == kModeConstScaled;        // scaled recurrence, constant gap penalties
     constexpr bool SCALEDG = MODE == kModeGeneralScaled;      // scaled recurrence, per-base gap penalties
     constexpr bool SCALED = SCALEDC || SCALEDG;
+    // FOLD (the scaled modes): pMM is folded into the prior table (prior' = prior * pMM, rounded once per row and base) and
+    // the gap weights are divided by it, so that M = prior' * (M_diag + g' * (X^_diag + Y^_diag)) -- add, fma, mul: FIVE
+    // FP32-pipe instructions per cell with the two fma of X^ and Y^ (per-base gaps: fma, fma, mul, no add).  The engine
+    // selects these modes only where pMM >= 0.8 (gap-open penalties >= Q10).
+    constexpr bool FOLD = SCALED;
     static_assert(!SCALED || !EXACT, "the scaled recurrence exists for the fast kernels (exact = the reference's operation order)");
     constexpr int KP = CONSTG ? 1 : K;    // per-row factor arrays collapse to one warp-uniform entry
     constexpr int SUBT = subtable_bytes(K, G);
@@ -467,6 +473,7 @@ forward_kernel(const KernelArgs args)
             pXXc   = P::splat(P::cg(args, 4));
         }
         __syncwarp();                     // previous sub / previous user of this warp's tables is done
+        if (FOLD && ZRESET) reinterpret_cast<uint32_t*>(stab + tables_bytes(K, G) - kZeroRowBytes)[lane] = 0u;
         {
 #pragma unroll
             for (int hf = 0; hf < NH; ++hf) {
@@ -503,9 +510,14 @@ forward_kernel(const KernelArgs args)
                                 mx_  = P::smul(gapm, pmy_up);                         // slot of pMX: weight of Y^ above-left
                                 my_  = P::sdiv(P::smul(yy, pmx_up), own_mx);          // slot of pMY: X^ self-transition
                                 gapm = P::smul(gapm, pmx_up);                         // weight of X^ above-left
+                                if (FOLD) { mx_ = P::sdiv(mx_, mm_); gapm = P::sdiv(gapm, mm_); }
                             }
                         } else {
                             yy = P::cg(args, 4);
+                        }
+                        if (FOLD) {                   // prior' = prior * pMM of the row
+                            const S mmv = CONSTG ? P::cg(args, 0) : mm_;
+                            mat = P::smul(mat, mmv); mis = P::smul(mis, mmv);
                         }
                     }
                     // prior table entry [haplotype base b][row]: half hf of an 8-byte V
@@ -619,14 +631,15 @@ forward_kernel(const KernelArgs args)
         V qM = inM, qX = inX, qY = inY;   // kSkew == 2: bottom row in flight (sent last step, used next step)
 
         const uint32_t tab_addr = (uint32_t)__cvta_generic_to_shared(my_tab);
+        const uint32_t zero_addr = (uint32_t)__cvta_generic_to_shared(stab + tables_bytes(K, G) - kZeroRowBytes);
+        (void)zero_addr;
         // products: EXACT ones honour the reference's flush-to-zero in both precisions (P::mulx)
         auto MUL = [](const V a, const V b) { return EXACT ? P::mulx(a, b) : P::mul(a, b); };
         // K cell updates of this lane's current column; `cb` is the column's stream byte
-        auto cells = [&](const uint32_t cb, const V fMM, const V fG, const V fYY, const V fMM0, const V fGX0) {
+        auto cells = [&](const uint32_t pa, const V fMM, const V fG, const V fYY, const V fMM0, const V fGX0) {
             // priors of this column: K entries of the sub-table the haplotype base names.  Issued
             // first; phase A below (4K FP32-pipe instructions) covers the LDS latency.
-            V prior[K + 1];
-            const uint32_t pa = tab_addr + (cb << 7);
+            V prior[K + 1];                   // pa: shared address of the lane's row in the sub-table of the column's base
 #pragma unroll
             for (int k = 0; k < K; k += 2) lds_2v<V>(pa + 8u * k, prior[k], prior[k + 1]);
             // Phase A: everything that reads the previous column's state (so every old value is dead
@@ -646,6 +659,11 @@ forward_kernel(const KernelArgs args)
                 if (EXACT) {
                     // reference operation order, unfused (avx-pairhmm-template.h:188)
                     t0[k] = P::addx(P::addx(MUL(dM, cMM), MUL(dX, cGX)), MUL(dY, cGY));
+                } else if (FOLD && SCALEDC) {
+                    // (a PACKED group's first lane receives zeros for M and X: see rotate)
+                    t0[k] = P::fma(P::add(dX, dY), cGY, dM);
+                } else if (FOLD) {
+                    t0[k] = P::fma(dY, cGY, P::fma(dX, cGX, dM));
                 } else {
                     t0[k] = P::fma(dY, cGY, P::fma(dX, cGX, MUL(dM, cMM)));
                 }
@@ -691,6 +709,7 @@ forward_kernel(const KernelArgs args)
             // SCALED: there is no product with pMX0 = 0 left to annihilate what the top lane receives (another group's
             // last row, or -- the shuffle has no source for lane 0 -- its own)
             if (SCALED && (PACKED || !ALIGNED)) rM = P::sel(top, top, P::splat(0), rM);
+            if (FOLD && PACKED) rX = P::sel(top, top, P::splat(0), rX);      // no zeroed factor left for it either
             if (kSkew == 2) {
                 inM = qM; inX = qX; inY = qY;
                 qM = rM; qX = rX; qY = rY;
@@ -767,9 +786,11 @@ forward_kernel(const KernelArgs args)
                     }
                     const V z = P::splat(0);
                     // a zero step reads the lane's own 'A' sub-table: any FINITE priors do (0 * prior must be 0)
-                    cells(zs ? 0u : bcur, zs ? z : pMM[0], zs ? z : pGAPM[0], zs ? z : pXXc, zs ? z : pMM0, zs ? z : pGAPX0);
+                    // FOLD: M = prior' * (...) has no factor left to zero -- the zero step reads a row of zero priors
+                    const uint32_t pa = (FOLD && zs) ? zero_addr : tab_addr + ((zs ? 0u : bcur) << 7);
+                    cells(pa, zs ? z : pMM[0], zs ? z : pGAPM[0], zs ? z : pXXc, zs ? z : pMM0, zs ? z : pGAPX0);
                 } else {
-                    if (bcur < 0x80u) cells(bcur, pMM[0], pGAPM[0], pXXc, pMM0, pGAPX0);
+                    if (bcur < 0x80u) cells(tab_addr + (bcur << 7), pMM[0], pGAPM[0], pXXc, pMM0, pGAPX0);
                     else if (bcur == (uint32_t)kStreamNext) boundary();
                 }
                 rotate();
@@ -778,7 +799,7 @@ forward_kernel(const KernelArgs args)
             for (; t < t_s; ++t) {
                 const uint32_t bcur = b_next;
                 b_next = lds_u8(bp + (uint32_t)(t + 1));
-                cells(bcur, pMM[0], pGAPM[0], pXXc, pMM0, pGAPX0);
+                cells(tab_addr + (bcur << 7), pMM[0], pGAPM[0], pXXc, pMM0, pGAPX0);
                 rotate();
             }
         }

@@ -444,7 +444,7 @@ def test_hunt_for_a_fast_vs_exact_rescue_flip(pkg, engine, exact_engine):
         flips = fast.rescued != exact.rescued
         d = np.abs(fast.log10 - exact.log10)
         assert np.nanmax(d) <= TOL32                                   # a flip never costs more than FP32-vs-FP64
-        assert (ulps[flips] <= 8).all()                                # and flips only ever happen AT the threshold
+        assert (ulps[flips] <= 16).all()                               # and flips only ever happen AT the threshold (2e-6 relative)
         assert np.array_equal(fast.rescued[~flips], exact.rescued[~flips])
         return fast, exact, ulps, flips
 
