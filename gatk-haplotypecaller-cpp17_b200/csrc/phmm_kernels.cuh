@@ -302,14 +302,16 @@ constexpr int kStreamNext = 0x80, kStreamIdle = 0x81, kStreamNext2 = 0x82;   // 
 // overflows or eats the underflow guard: see where s_inity is filled).  Then
 //     M[r][c]  = prior * (pMM * M[r-1][c-1] + g * (X^[r-1][c-1] + Y^[r-1][c-1])),   g = pGAPM * pMX  (= pGAPM * pMY)
 //     X^[r][c] = M[r-1][c] + pXX * X^[r-1][c]          Y^[r][c] = M[r][c-1] + pYY * Y^[r][c-1]
-// -- the products M * pMX and M * pMY are gone: SIX FP32-pipe instructions per cell (mul, fma, fma, mul, fma, fma)
+// -- the products M * pMX and M * pMY are gone: six FP32-pipe instructions per cell (mul, fma, fma, mul, fma, fma)
 // instead of the eight of the reference's expression (seven in MODE 2), the M * p array of MODE 2 and its K register
-// pairs too; the final sum is sum(M) + pMX * sum(X^).  Same recurrence in exact arithmetic; in floating point it
+// pairs too; the final sum is sum(M) + pMX * sum(X^).  With pMM folded into the prior table on top (FOLD, below:
+// M = prior' * (M_diag + g' * (X^_diag + Y^_diag))) it is FIVE: add, fma, mul, fma, fma.  Same recurrence in exact arithmetic; in floating point it
 // rounds differently from the reference's operation order (as the FMA-contracted MODE 2 already does), well inside
 // the 1e-4 bar on the final log10 -- measured, with the number of rescue decisions it moves at the threshold, in
 // DESIGN.md section 4.1.  Row 0 of the reference (Y = INITIAL_CONSTANT / haplen) becomes Y^ = that / pMY.
 // MODE 4 is the same idea for PER-BASE gap penalties: row r carries X^ = X / pMX_r and Y^ = Y / pMY_r, its five
-// register-resident factors become pMM_r, pGAPM_r pMX_{r-1}, pGAPM_r pMY_{r-1}, pXX_r pMX_{r-1} / pMX_r and pYY_r, and
+// register-resident factors become pMM_r (folded into the row's priors: FOLD), pGAPM_r pMX_{r-1}, pGAPM_r pMY_{r-1} (both
+// divided by pMM_r), pXX_r pMX_{r-1} / pMX_r and pYY_r, and
 // the final sum is sum(M) + pMX_R sum(X^).  M itself is unscaled and the reference's row 0 keeps its own Y
 // (its "pMY" is taken as 1), so nothing moves towards overflow or underflow as long as neighbouring rows' gap-open
 // penalties do not differ by more than the engine checks for (phmm_engine.cu: scaled_general_is_safe).
