@@ -1138,7 +1138,7 @@ int stage_launch(DeviceCtx& dc, Slot& s, bool exact, bool use_double, bool do_la
         int rcp = plan_part(&view, 0, n_regions, out0, dc.sm_count, dc.last_rescue_frac, pool, p, plan, err, dc.fp64_first_opt);
         if (rcp) return rcp;
         p.g0 = g0; p.g1 = g1; p.out0 = out0; p.read0 = c.read0;
-        // constant gap penalties with i == d: the lane-aligned jobs take the scaled recurrence (six FP32-pipe
+        // constant gap penalties with i == d: every job takes the scaled recurrence (five FP32-pipe
         // instructions per cell) unless the engine was asked for the reference's operation order
         // (not for gap-open penalties beyond Q96: M^ = s M with s = min(1, 64 H pMX) must stay a normal float wherever
         //  M matters, i.e. down to ~1e-30 of the 2^120 scale, which needs H pMX >= 2e-10; the reference's 'I' is 5e-8)

@@ -83,8 +83,9 @@ typedef struct phmm_options {
                                    Ignored (never) with exact_fp32, whose raw FP32 sums are part of the contract. */
     int32_t recurrence;         /* arithmetic of the default (non-exact) FP32 / FP64 kernels for constant gap penalties
                                    with i == d -- the reference's only case.  0: the SCALED recurrence where the layout
-                                   allows it (carries X / pMX and Y / pMY: six FP32-pipe instructions per cell instead
-                                   of seven; same mathematics, different rounding, well inside 1e-4 on the log10).
+                                   allows it (carries X / pMX and Y / pMY and folds pMM into the priors: five FP32-pipe
+                                   instructions per cell instead of seven; same mathematics, different rounding, well
+                                   inside 1e-4 on the log10; gap-open penalties Q10..Q96, the reference order otherwise).
                                    1: the reference's operation order, FMA-contracted (round 1's kernels).
                                    exact_fp32 overrides both.  Environment: PHMM_REFERENCE_ORDER=1 forces 1. */
 } phmm_options;
