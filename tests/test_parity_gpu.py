@@ -510,7 +510,8 @@ def test_scaled_and_reference_order_recurrences_agree(pkg, engine, oracle, name,
     assert _maxerr(got.log10[~keep], other.log10[~keep]) <= 1e-9
 
 
-@pytest.mark.parametrize("gap", [(40, 40, 35), (96, 96, 43), (100, 100, 43), (127, 127, 60), (33, 33, 43), (73, 73, 12)])
+@pytest.mark.parametrize("gap", [(40, 40, 35), (96, 96, 43), (100, 100, 43), (127, 127, 60), (33, 33, 43), (73, 73, 12),
+                                 (10, 10, 30), (9, 9, 30), (3, 3, 20)])     # Q10: the last folded one; below: reference order (pMM -> 0)
 def test_scaled_recurrence_over_the_range_of_constant_gap_penalties(pkg, engine, oracle, gap):
     """The scale split of the scaled recurrence depends on the gap-open probability (row 0 must not overflow, M^ must
     not underflow): from a cheap gap (Q40 raw byte: s = 1) over the reference's own 'I' to penalties beyond Q96, where
