@@ -510,6 +510,25 @@ def test_scaled_and_reference_order_recurrences_agree(pkg, engine, oracle, name,
     assert _maxerr(got.log10[~keep], other.log10[~keep]) <= 1e-9
 
 
+@pytest.mark.parametrize("i_range,c_range", [((10, 21), (10, 30)),     # MODE 4 (folded): spread 10 <= c_min, i_min = 10
+                                             ((4, 15), (10, 30)),      # i_min < 10 (pMM down to 0.2): MODE 0
+                                             ((0, 4), (10, 30)),       # pMM = 0 rows: MODE 0
+                                             ((30, 70), (10, 30)),     # spread 39 > c_min + 10: MODE 0
+                                             ((40, 60), (25, 60))])    # MODE 4, wide
+def test_per_base_gap_penalties_either_side_of_the_scaled_mode_guards(pkg, engine, oracle, i_range, c_range):
+    """MODE 4 (scaled + folded, per-base gap penalties) is selected only where the engine's guards hold
+    (phmm_engine.cu: scaled_general_is_safe -- continuation >= Q10, gap-open spread <= c_min + 10, gap-open >= Q10
+    because the row's weights are divided by its pMM); everything else runs MODE 0.  Parity on both sides."""
+    b = pkg.synth.random_small(77, n_regions=16, max_reads=40, max_haps=8, max_read_len=200, max_hap_len=300, general_gaps=True)
+    assert b.explicit_gaps
+    rng = np.random.default_rng(i_range[0] * 131 + c_range[0])
+    n = len(b.read_i)
+    b.read_i[:] = rng.integers(i_range[0], i_range[1], n)
+    b.read_d[:] = rng.integers(i_range[0], i_range[1], n)
+    b.read_c[:] = rng.integers(c_range[0], c_range[1], n)
+    check(engine.compute(b), oracle.batch(b, threads=8), what=f"per-base gaps i,d in {i_range}, c in {c_range}")
+
+
 @pytest.mark.parametrize("gap", [(40, 40, 35), (96, 96, 43), (100, 100, 43), (127, 127, 60), (33, 33, 43), (73, 73, 12),
                                  (10, 10, 30), (9, 9, 30), (3, 3, 20)])     # Q10: the last folded one; below: reference order (pMM -> 0)
 def test_scaled_recurrence_over_the_range_of_constant_gap_penalties(pkg, engine, oracle, gap):
